@@ -1,0 +1,121 @@
+/*
+ * ultra_rspmm.h -- C ABI of the Blackwell-native (sm_100a) generalized relational SpMM ("rspmm").
+ *
+ * This is the drop-in boundary for the ONE hot path of DeepGraphLearning/ULTRA:
+ *     out[i,:] = AGG_{e : edge_index[0,e]==i}  w_e * ( relation[type_e,:] (*|+) input[edge_index[1,e],:] )
+ * It replaces the 24 pybind11 entry points  rspmm_{add,min,max}_{mul,add}_{forward,backward}_{cpu,cuda}
+ * of the reference (/root/reference/ultra/rspmm/source/rspmm.cpp:256-283, declared in rspmm.h:22-105) with
+ * a plan-based interface: the per-call argsort + sortedness assert + ind2ptr of the reference
+ * (/root/reference/ultra/rspmm/rspmm.py:15-17,174-178; rspmm.cpp:40-48) become ONE plan build per graph.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; ultra_rspmm_last_error() gives the message
+ *     (thread-local).  No C++ exceptions cross the ABI.
+ *   - the library owns NO device memory: the caller allocates every device buffer (workspace, scratch,
+ *     outputs).  Plans are small host objects holding pointers into the caller's workspace.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*); forward/backward
+ *     never synchronise the host and are CUDA-graph capturable.  plan_build synchronises `stream` once.
+ *   - dtype: ULTRA_RSPMM_F32 or ULTRA_RSPMM_F64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES,
+ *     rspmm.cu:251,313,332).  Indices are int64 at the boundary (reference convention, rspmm.cpp:22),
+ *     int32 inside the plan.
+ *   - there is NO CPU implementation behind this ABI (north star: "no CPU fallback").
+ */
+#ifndef ULTRA_RSPMM_H_
+#define ULTRA_RSPMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* NaryOp of the reference (operator.cuh:42-80) */
+enum { ULTRA_RSPMM_SUM_ADD = 0, ULTRA_RSPMM_SUM_MIN = 1, ULTRA_RSPMM_SUM_MAX = 2 };
+/* BinaryOp of the reference (operator.cuh:13-40): MUL = distmult, ADD = transe */
+enum { ULTRA_RSPMM_MUL_MUL = 0, ULTRA_RSPMM_MUL_ADD = 1 };
+enum { ULTRA_RSPMM_F32 = 0, ULTRA_RSPMM_F64 = 1 };
+
+typedef struct ultra_rspmm_plan ultra_rspmm_plan; /* opaque host object */
+
+/* Library / build identification ("ultra_rspmm sm_100a <version>"). */
+const char *ultra_rspmm_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char *ultra_rspmm_last_error(void);
+
+/* Bytes of device workspace a plan for (num_node, num_edge, num_relation) needs (upper bound). */
+size_t ultra_rspmm_plan_workspace_bytes(int64_t num_node, int64_t num_edge, int64_t num_relation);
+
+/*
+ * Build the graph plan: replaces generalized_rspmm's per-call `key.argsort()` + gathers (rspmm.py:174-178),
+ * the `assert (key.diff() >= 0).all()` host sync (rspmm.py:15-17) and ind2ptr (rspmm.cpp:40-48).
+ *   edge_index : device int64 (2, num_edge) row-major; [0]=aggregating node (row), [1]=gathered node (col)
+ *   edge_type  : device int64 (num_edge)
+ *   workspace  : device buffer of >= ultra_rspmm_plan_workspace_bytes() bytes, 256-byte aligned; must stay
+ *                alive and untouched for the life of the plan
+ * Produces int32 CSR by row (forward), by col (input_grad), by relation (relation_grad), each with its
+ * edge-balanced work-item list.  Fails if any index is out of range (UB in the reference, rspmm.cu:234-236).
+ */
+int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_index, const int64_t *edge_type,
+                           int64_t num_node, int64_t num_edge, int64_t num_relation, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan);
+
+/* 1 if the caller's edge order was already sorted by the reference key (rspmm.py:15-17), else 0. */
+int ultra_rspmm_plan_input_sorted(const ultra_rspmm_plan *plan);
+
+/* Plan facts: what=0 num_node, 1 num_edge, 2 num_relation, 3 fwd work items, 4 fwd partial slots,
+ * 5 input_grad partial slots, 6 relation_grad partial slots, 7 SM count used for grid sizing. */
+int64_t ultra_rspmm_plan_info(const ultra_rspmm_plan *plan, int what);
+
+/* Bytes of device scratch (split-row partials) forward/backward need for feature width `dim`. */
+size_t ultra_rspmm_scratch_bytes(const ultra_rspmm_plan *plan, int64_t dim, int dtype);
+
+/*
+ * Bind per-call edge weights: permutes `edge_weight` (device, caller edge order, length num_edge, dtype)
+ * into the plan's three edge orders inside the plan workspace.  Must precede forward/backward whenever the
+ * weight VALUES changed.  edge_weight == NULL selects the all-ones specialisation (ULTRA's only case,
+ * models.py:68,144,225), which is bit-identical because 1*x == x.
+ */
+int ultra_rspmm_set_edge_weight(ultra_rspmm_plan *plan, const void *edge_weight, int dtype, void *stream);
+
+/*
+ * Forward: replaces rspmm_{add,min,max}_{mul,add}_forward_cuda (rspmm.cu:216-267, kernel :21-83).
+ *   relation (num_relation, dim), input (num_node, dim), output (num_node, dim): device, row-major, dtype
+ *   scratch : device buffer of >= ultra_rspmm_scratch_bytes(plan, dim, dtype) (may be NULL if that is 0)
+ * Every element of `output` is written (empty rows get the Nary identity 0 / +MAX / -MAX, operator.cuh:53,66,79).
+ */
+int ultra_rspmm_forward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                        const void *input, void *output, int64_t dim, void *scratch, size_t scratch_bytes,
+                        void *stream);
+
+/*
+ * Backward: replaces rspmm_{...}_backward_cuda (rspmm.cu:269-351, kernels :85-214) WITHOUT atomics:
+ *   input_grad    = gather-reduce over the by-col CSR, relation_grad = gather-reduce over the by-relation CSR,
+ *   weight_grad   = per-edge dot product, written in the CALLER's edge order; pass NULL to skip it (the
+ *                   reference leaves zeros unless edge_weight.requires_grad, rspmm.cu:295,312-331).
+ * Every element of relation_grad / input_grad (/ weight_grad) is written; no pre-zeroing needed.
+ */
+int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                         const void *input, const void *output, const void *output_grad, void *weight_grad,
+                         void *relation_grad, void *input_grad, int64_t dim, void *scratch,
+                         size_t scratch_bytes, void *stream);
+
+/*
+ * End-to-end forward from HOST buffers (pinned for full speed): relation/input/output live in host memory;
+ * the call pipelines column slabs  H2D copy -> kernel -> D2H copy  on three internal streams forked from and
+ * joined back to `stream`.  `staging` is a caller-provided device buffer; ultra_rspmm_host_staging_bytes()
+ * gives the size for a given slab width.  Mirrors what the reference does when handed CPU tensors
+ * (dispatch on input.device.type, rspmm.py:19-22) -- except the arithmetic still runs on the GPU.
+ */
+size_t ultra_rspmm_host_staging_bytes(const ultra_rspmm_plan *plan, int64_t dim, int64_t slab_dim, int dtype);
+int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype,
+                             const void *h_relation, const void *h_input, void *h_output, int64_t dim,
+                             int64_t slab_dim, void *staging, size_t staging_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRA_RSPMM_H_ */

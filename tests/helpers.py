@@ -1,0 +1,68 @@
+"""Shared helpers for the parity tests (test infrastructure; may use oracle/)."""
+import os
+
+import numpy as np
+import torch
+
+import oracle
+
+OPS = [(s, m) for s in ("add", "min", "max") for m in ("mul", "add")]
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rspmm_golden.npz")
+GOLDEN_CASES = ["rand_f32", "rand_f64", "hub_f32", "ties_f32", "oddD_f32", "unitw_f32"]
+
+
+def load_golden():
+    return np.load(GOLDEN)
+
+
+def random_case(seed, N, E, R, D, dtype=torch.float32, hub=0, unit_weight=False, isolated=2):
+    g = torch.Generator().manual_seed(seed)
+    hi = max(N - isolated, 1)
+    ei = torch.randint(0, hi, (2, E), generator=g)
+    if hub:
+        ei[0, :hub] = min(1, hi - 1)
+    et = torch.randint(0, R, (E,), generator=g)
+    rel = torch.randn(R, D, generator=g, dtype=dtype)
+    x = torch.randn(N, D, generator=g, dtype=dtype)
+    w = torch.ones(E, dtype=dtype) if unit_weight else torch.rand(E, generator=g, dtype=dtype) + 0.5
+    og = torch.randn(N, D, generator=g, dtype=dtype)
+    return ei, et, w, rel, x, og
+
+
+def oracle_all(sum, mul, ei, et, w, rel, x, og=None):
+    """C oracle on unsorted CPU tensors; grads returned in the caller's edge order."""
+    sei, stt, sw, order = oracle.sort_edges(ei.numpy(), et.numpy(), w.numpy())
+    out = oracle.c_forward(sum, mul, sei, stt, sw, rel.numpy(), x.numpy())
+    if og is None:
+        return torch.from_numpy(out)
+    wg, rg, ig = oracle.c_backward(sum, mul, sei, stt, sw, rel.numpy(), x.numpy(), out, og.numpy())
+    wg_caller = np.empty_like(wg)
+    wg_caller[order] = wg
+    return tuple(torch.from_numpy(a) for a in (out, wg_caller, rg, ig))
+
+
+def assert_close_ref(actual, expected, what, rtol=1e-5):
+    """north-star tolerance: 1e-5 fp32 relative, with atol = 1e-5 * max|expected| (SURVEY.md section 8d:
+    tree-order vs sequential fp32 sums differ by ~1e-7 * sum|terms|, so a pure relative test is ill-posed under
+    cancellation).  fp64 uses 1e-12."""
+    expected = torch.as_tensor(expected)
+    actual = torch.as_tensor(actual).cpu()
+    if expected.dtype == torch.float64:
+        rtol = 1e-12
+    scale = float(expected.abs().max()) if expected.numel() else 0.0
+    if not np.isfinite(scale) or scale > 1e30:  # +-FLT_MAX identities of empty rows: compare finite part by value
+        fin = expected.abs() < 1e30
+        assert torch.equal(actual[~fin], expected[~fin]), what + ": identity (empty-row) entries differ"
+        if fin.any():
+            scale = float(expected[fin].abs().max())
+            torch.testing.assert_close(actual[fin], expected[fin], rtol=rtol, atol=rtol * scale, msg=lambda m: what + ": " + m)
+        return
+    torch.testing.assert_close(actual, expected, rtol=rtol, atol=rtol * scale, msg=lambda m: what + ": " + m)
+
+
+def assert_equal_values(actual, expected, what):
+    """bit-exact by value (min/max forward involves no re-association; -0.0 == +0.0 compare equal)."""
+    actual = torch.as_tensor(actual).cpu()
+    expected = torch.as_tensor(expected)
+    assert actual.shape == expected.shape, what
+    assert bool((actual == expected).all()), "%s: %d mismatching elements" % (what, int((actual != expected).sum()))

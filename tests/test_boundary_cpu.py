@@ -1,0 +1,105 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/ultra_rspmm.h declares, and the Python
+boundary mirrors the reference's names and error behaviour (no compute calls - there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from ultra_b200 import build, _capi
+    build.build()  # nvcc cross-compiles sm_100a without a GPU
+    return _capi
+
+
+def test_header_symbols_exported(capi):
+    header = open(os.path.join(ROOT, "include", "ultra_rspmm.h")).read()
+    declared = set(re.findall(r"\b(ultra_rspmm_[a-z_]+)\s*\(", header))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    handle = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert capi.lib().ultra_rspmm_version().startswith(b"ultra_rspmm sm_100a")
+
+
+def test_library_is_sm100a_only(capi):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_workspace_bytes_is_pure_host(capi):
+    lib = capi.lib()
+    small = lib.ultra_rspmm_plan_workspace_bytes(10, 100, 3)
+    big = lib.ultra_rspmm_plan_workspace_bytes(14541, 544230, 474)
+    assert 0 < small < big < 1 << 30
+
+
+def test_reference_surface_names():
+    from ultra_b200 import rspmm as mod
+    from ultra_b200.rspmm import rspmm as inner
+    for s in ("Add", "Min", "Max"):
+        for m in ("Mul", "Add"):
+            cls = getattr(mod, "RSPMM%s%sFunction" % (s, m))
+            assert issubclass(cls, torch.autograd.Function)
+            assert hasattr(inner, "RSPMM%s%sFunction" % (s, m))
+    import inspect
+    sig = inspect.signature(mod.generalized_rspmm)
+    assert list(sig.parameters) == ["edge_index", "edge_type", "edge_weight", "relation", "input", "sum", "mul"]
+    assert sig.parameters["sum"].default == "add" and sig.parameters["mul"].default == "mul"
+
+
+def test_unknown_op_raises_value_error():
+    from ultra_b200.rspmm import generalized_rspmm
+    a = torch.zeros(2, 3, dtype=torch.long)
+    with pytest.raises(ValueError, match="No generalized rspmm implementation found for summation `mean`"):
+        generalized_rspmm(a, a[0], torch.ones(3), torch.ones(2, 4), torch.ones(3, 4), sum="mean")
+    with pytest.raises(ValueError, match="multiplication `rotate`"):
+        generalized_rspmm(a, a[0], torch.ones(3), torch.ones(2, 4), torch.ones(3, 4), mul="rotate")
+
+
+@pytest.mark.parametrize("mutate,match", [
+    (lambda a: a.update(edge_index=a["edge_index"].int()), "expected scalar type Long"),
+    (lambda a: a.update(edge_index=a["edge_index"][:1]), "size 2 at dimension 0"),
+    (lambda a: a.update(edge_type=a["edge_type"][:2]), "argument #2 'edge_type'"),
+    (lambda a: a.update(edge_weight=a["edge_weight"][:2]), "argument #3 'edge_weight'"),
+    (lambda a: a.update(relation=a["relation"][:, :3]), "argument #4 'relation'"),
+    (lambda a: a.update(relation=a["relation"].double()), "same type"),
+    (lambda a: a.update(input=a["input"][0]), "argument #5 'input'"),
+    (lambda a: a.update(input=a["input"].half(), relation=a["relation"].half(), edge_weight=a["edge_weight"].half()),
+     "not implemented for 'Half'"),
+])
+def test_argument_checks_raise_runtime_error(mutate, match):
+    """Same situations as rspmm_forward_check (/root/reference/ultra/rspmm/source/rspmm.cpp:15-28)."""
+    from ultra_b200.rspmm import generalized_rspmm
+    args = dict(edge_index=torch.zeros(2, 3, dtype=torch.long), edge_type=torch.zeros(3, dtype=torch.long),
+                edge_weight=torch.ones(3), relation=torch.ones(2, 4), input=torch.ones(3, 4))
+    mutate(args)
+    with pytest.raises(RuntimeError, match=match):
+        generalized_rspmm(**args)
+
+
+def test_no_cpu_fallback_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from ultra_b200.rspmm import generalized_rspmm
+    a = torch.zeros(2, 3, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        generalized_rspmm(a, a[0], torch.ones(3), torch.ones(2, 4), torch.ones(3, 4))
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or /root/reference)."""
+    pkg = os.path.join(ROOT, "ultra_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "oracle/_ref" not in src and "rspmm_ref" not in src, f

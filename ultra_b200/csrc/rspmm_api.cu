@@ -1,0 +1,363 @@
+// rspmm_api.cu -- extern "C" surface declared in include/ultra_rspmm.h: argument checks, kernel selection and
+// launch geometry.  Replaces the host launchers of the reference (rspmm.cu:216-267 forward, :269-351 backward).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/ultra_rspmm.h"
+#include "rspmm_kernels.cuh"
+#include "rspmm_plan.h"
+
+namespace ultra {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (expr);                                                            \
+        if (err__ != cudaSuccess) {                                                            \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(err__));                  \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+constexpr size_t kSlabSmemLimit = 100 * 1024;  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
+
+template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
+    if (D % VecN<T>::value != 0) return false;
+    for (const void *p : ptrs)
+        if (p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
+    return true;
+}
+
+// ---- one segment pass (tiled kernel + fix-up, or the generic kernel) -------------------------------------
+template <typename T, int MODE, int SUM, int MUL>
+int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input, const T *output,
+                const T *outgrad, T *dst, T *scratch, int64_t D, cudaStream_t stream) {
+    using Nd = Needs<MODE, SUM, MUL>;
+    const SegOrder &so = plan->ord[MODE];
+    const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
+    if (so.num_seg == 0 || D == 0) return 0;
+
+    if (!vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch})) {
+        const long long total = (long long)so.num_seg * D;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)plan->sm_count * 16);
+        seg_reduce_generic_kernel<T, MODE, SUM, MUL><<<blocks, 256, 0, stream>>>(
+            so.meta, w, so.seg_ptr, so.num_seg, relation, input, output, outgrad, dst, (int)D);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+
+    constexpr int V = VecN<T>::value;
+    constexpr int TILE = kLanesPerEdge * V;
+    SegParams<T> p;
+    p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.nonempty = so.nonempty; p.items = so.items;
+    p.num_warp_items = so.num_items / kSubPerWarp;
+    p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
+    p.dst = dst; p.partial = scratch;
+    p.D = (int)D; p.R = (int)plan->R;
+    p.num_tiles = (int)((D + TILE - 1) / TILE);
+
+    if (p.num_warp_items > 0) {
+        const int ctas = plan->sm_count * 2;
+        // items per warp per unit: 2 when that still leaves every CTA several units
+        int ipw = 2;
+        auto units_per_tile = [&](int k) { return (p.num_warp_items + kCtaWarps * k - 1) / (kCtaWarps * k); };
+        if ((long long)units_per_tile(ipw) * p.num_tiles < 4LL * ctas) ipw = 1;
+        p.items_per_warp = ipw;
+        p.units_per_tile = units_per_tile(ipw);
+        p.total_units = (long long)p.units_per_tile * p.num_tiles;
+        // tile-major walk: each CTA takes `run` consecutive units, so ~ctas*run/units_per_tile tiles are in
+        // flight; keep their gathered footprint (segments' source rows x 128 B) within a fraction of L2.
+        const size_t l2_budget = plan->l2_bytes ? plan->l2_bytes / 4 : (size_t)24 << 20;
+        const size_t rows_gathered = (size_t)std::max<int64_t>(plan->N, 1);
+        const double tiles_in_flight = std::max(1.0, (double)l2_budget / ((double)rows_gathered * kTileBytes));
+        long long run = (long long)(tiles_in_flight * p.units_per_tile / ctas);
+        run = std::max<long long>(1, std::min<long long>(run, p.units_per_tile));
+        p.run = (int)run;
+        const long long nblk = (p.total_units + p.run - 1) / p.run;
+        const int grid = (int)std::min<long long>(nblk, ctas);
+
+        const size_t slab = (size_t)plan->R * kTileBytes;
+        const bool rel_smem = Nd::rel && slab <= kSlabSmemLimit;
+        if (rel_smem) {
+            auto kern = seg_reduce_kernel<T, MODE, SUM, MUL, true>;
+            static thread_local int attr_set_for = -1;  // per (instantiation, thread); cheap to redo per device
+            if (attr_set_for != plan->device) {
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemLimit));
+                attr_set_for = plan->device;
+            }
+            kern<<<grid, kCtaThreads, slab, stream>>>(p);
+        } else {
+            seg_reduce_kernel<T, MODE, SUM, MUL, false><<<grid, kCtaThreads, 0, stream>>>(p);
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (so.num_fix > 0) {
+        const int ncc = (int)((D + 32 * V - 1) / (32 * V));
+        const long long warps = (long long)so.num_fix * ncc;
+        const int blocks = (int)((warps * 32 + 255) / 256);
+        fixup_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix, so.num_fix, scratch, dst, (int)D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <typename T, int SUM, int MUL>
+int forward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, void *output, int64_t D,
+              void *scratch, cudaStream_t stream) {
+    return launch_pass<T, FWD, SUM, MUL>(plan, (const T *)relation, (const T *)input, nullptr, nullptr, (T *)output,
+                                         (T *)scratch, D, stream);
+}
+
+template <typename T, int SUM, int MUL>
+int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, const void *output,
+               const void *outgrad, void *wgrad, void *rgrad, void *igrad, int64_t D, void *scratch,
+               cudaStream_t stream) {
+    int rc = launch_pass<T, BWD_IN, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
+                                              (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream);
+    if (rc) return rc;
+    rc = launch_pass<T, BWD_REL, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
+                                           (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream);
+    if (rc) return rc;
+    if (wgrad != nullptr && plan->E > 0) {
+        const SegOrder &so = plan->ord[FWD];
+        const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
+        const long long threads = (long long)plan->E * 32;
+        wgrad_kernel<T, SUM, MUL><<<(int)((threads + 255) / 256), 256, 0, stream>>>(
+            so.meta, so.eid, plan->row_of_edge, w, (const T *)relation, (const T *)input, (const T *)output,
+            (const T *)outgrad, (T *)wgrad, (int)plan->E, (int)D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+#define DISPATCH_OPS(FN, T, ...)                                                          \
+    switch (sum_op * 2 + mul_op) {                                                        \
+        case 0: return FN<T, S_ADD, M_MUL>(__VA_ARGS__);                                  \
+        case 1: return FN<T, S_ADD, M_ADD>(__VA_ARGS__);                                  \
+        case 2: return FN<T, S_MIN, M_MUL>(__VA_ARGS__);                                  \
+        case 3: return FN<T, S_MIN, M_ADD>(__VA_ARGS__);                                  \
+        case 4: return FN<T, S_MAX, M_MUL>(__VA_ARGS__);                                  \
+        case 5: return FN<T, S_MAX, M_ADD>(__VA_ARGS__);                                  \
+    }
+
+int check_common(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, int64_t dim) {
+    if (plan == nullptr) { set_error("null plan"); return 1; }
+    if (sum_op < 0 || sum_op > 2 || mul_op < 0 || mul_op > 1) { set_error("unknown sum_op / mul_op"); return 1; }
+    if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) { set_error("unknown dtype"); return 1; }
+    if (dim < 0 || dim >= (int64_t(1) << 31)) { set_error("dim out of range"); return 1; }
+    if (!plan->unit_weight && plan->w_dtype != dtype) {
+        set_error("edge weights were bound with a different dtype than relation/input (checkAllSameType)");
+        return 1;
+    }
+    return 0;
+}
+
+size_t scratch_bytes(const ultra_rspmm_plan *plan, int64_t dim, int dtype) {
+    int slots = 0;
+    for (int o = 0; o < 3; o++) slots = std::max(slots, plan->ord[o].num_slots);
+    return (size_t)slots * (size_t)dim * (dtype == ULTRA_RSPMM_F32 ? 4 : 8);
+}
+
+}  // namespace
+}  // namespace ultra
+
+using namespace ultra;
+
+extern "C" {
+
+const char *ultra_rspmm_version(void) { return "ultra_rspmm sm_100a 0.1.0"; }
+
+const char *ultra_rspmm_last_error(void) { return g_last_error.c_str(); }
+
+size_t ultra_rspmm_plan_workspace_bytes(int64_t num_node, int64_t num_edge, int64_t num_relation) {
+    return plan_workspace_bytes(num_node, num_edge, num_relation);
+}
+
+int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_index, const int64_t *edge_type,
+                           int64_t num_node, int64_t num_edge, int64_t num_relation, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    if (plan_out == nullptr) { set_error("plan_out is null"); return 1; }
+    *plan_out = nullptr;
+    return plan_build(plan_out, edge_index, edge_type, num_node, num_edge, num_relation, workspace,
+                      workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan) { delete plan; }
+
+int ultra_rspmm_plan_input_sorted(const ultra_rspmm_plan *plan) { return plan ? plan->input_sorted : 0; }
+
+int64_t ultra_rspmm_plan_info(const ultra_rspmm_plan *plan, int what) {
+    if (plan == nullptr) return -1;
+    switch (what) {
+        case 0: return plan->N;
+        case 1: return plan->E;
+        case 2: return plan->R;
+        case 3: return plan->ord[0].num_items;
+        case 4: return plan->ord[0].num_slots;
+        case 5: return plan->ord[1].num_slots;
+        case 6: return plan->ord[2].num_slots;
+        case 7: return plan->sm_count;
+    }
+    return -1;
+}
+
+size_t ultra_rspmm_scratch_bytes(const ultra_rspmm_plan *plan, int64_t dim, int dtype) {
+    return plan ? scratch_bytes(plan, dim, dtype) : 0;
+}
+
+int ultra_rspmm_set_edge_weight(ultra_rspmm_plan *plan, const void *edge_weight, int dtype, void *stream_) {
+    if (plan == nullptr) { set_error("null plan"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (edge_weight == nullptr) { plan->unit_weight = true; plan->w_dtype = -1; return 0; }
+    if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) { set_error("unknown dtype"); return 1; }
+    plan->unit_weight = false;
+    plan->w_dtype = dtype;
+    if (plan->E == 0) return 0;
+    const int E = (int)plan->E, blocks = (E + 255) / 256;
+    CUDA_TRY(cudaMemsetAsync(plan->w_nonunit, 0, sizeof(int), stream));
+    if (dtype == ULTRA_RSPMM_F32)
+        permute_weight_kernel<float><<<blocks, 256, 0, stream>>>(
+            (const float *)edge_weight, plan->ord[0].eid, plan->ord[1].eid, plan->ord[2].eid,
+            (float *)plan->ord[0].w, (float *)plan->ord[1].w, (float *)plan->ord[2].w, E, plan->w_nonunit);
+    else
+        permute_weight_kernel<double><<<blocks, 256, 0, stream>>>(
+            (const double *)edge_weight, plan->ord[0].eid, plan->ord[1].eid, plan->ord[2].eid,
+            (double *)plan->ord[0].w, (double *)plan->ord[1].w, (double *)plan->ord[2].w, E, plan->w_nonunit);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ultra_rspmm_forward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                        const void *input, void *output, int64_t dim, void *scratch, size_t scratch_bytes_,
+                        void *stream_) {
+    if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
+    if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("forward: scratch too small"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype == ULTRA_RSPMM_F32) {
+        DISPATCH_OPS(forward_t, float, plan, relation, input, output, dim, scratch, stream)
+    } else {
+        DISPATCH_OPS(forward_t, double, plan, relation, input, output, dim, scratch, stream)
+    }
+    return 1;
+}
+
+int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                         const void *input, const void *output, const void *output_grad, void *weight_grad,
+                         void *relation_grad, void *input_grad, int64_t dim, void *scratch, size_t scratch_bytes_,
+                         void *stream_) {
+    if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
+    if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("backward: scratch too small"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype == ULTRA_RSPMM_F32) {
+        DISPATCH_OPS(backward_t, float, plan, relation, input, output, output_grad, weight_grad, relation_grad,
+                     input_grad, dim, scratch, stream)
+    } else {
+        DISPATCH_OPS(backward_t, double, plan, relation, input, output, output_grad, weight_grad, relation_grad,
+                     input_grad, dim, scratch, stream)
+    }
+    return 1;
+}
+
+// ---- end-to-end from host buffers: column slabs pipelined H2D -> kernel -> D2H ------------------------------
+size_t ultra_rspmm_host_staging_bytes(const ultra_rspmm_plan *plan, int64_t dim, int64_t slab_dim, int dtype) {
+    if (plan == nullptr || slab_dim <= 0) return 0;
+    const size_t es = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    slab_dim = std::min(slab_dim, std::max<int64_t>(dim, 1));
+    // double-buffered {relation slab, input slab, output slab, scratch}
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t per = up((size_t)plan->R * slab_dim * es) + 2 * up((size_t)plan->N * slab_dim * es) +
+                       up(scratch_bytes(plan, slab_dim, dtype));
+    return 2 * per;
+}
+
+int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype,
+                             const void *h_relation, const void *h_input, void *h_output, int64_t dim,
+                             int64_t slab_dim, void *staging, size_t staging_bytes, void *stream_) {
+    if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
+    if (slab_dim <= 0) { set_error("forward_host: slab_dim must be positive"); return 1; }
+    slab_dim = std::min(slab_dim, std::max<int64_t>(dim, 1));
+    if (staging_bytes < ultra_rspmm_host_staging_bytes(plan, dim, slab_dim, dtype)) {
+        set_error("forward_host: staging too small");
+        return 1;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t es = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    const size_t N = (size_t)plan->N, R = (size_t)plan->R;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t sb = scratch_bytes(plan, slab_dim, dtype);
+    const size_t per = up(R * slab_dim * es) + 2 * up(N * slab_dim * es) + up(sb);
+    char *base = static_cast<char *>(staging);
+    struct Buf { char *rel, *in, *out, *scr; } buf[2];
+    for (int b = 0; b < 2; b++) {
+        char *p = base + (size_t)b * per;
+        buf[b].rel = p; p += up(R * slab_dim * es);
+        buf[b].in = p; p += up(N * slab_dim * es);
+        buf[b].out = p; p += up(N * slab_dim * es);
+        buf[b].scr = p;
+    }
+    // three lanes: copy-in, compute, copy-out; events chain them per slab and protect buffer reuse
+    cudaStream_t s_in, s_k, s_out;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    cudaEvent_t ev_start, ev_in[2], ev_k[2], ev_out[2], ev_done;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ev_start, stream));
+    CUDA_TRY(cudaStreamWaitEvent(s_in, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s_k, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s_out, ev_start, 0));
+    int rc = 0;
+    int it = 0;
+    for (int64_t c0 = 0; c0 < dim && rc == 0; c0 += slab_dim, it++) {
+        const int b = it & 1;
+        const int64_t wd = std::min(slab_dim, dim - c0);
+        const size_t wbytes = (size_t)wd * es, pitch_h = (size_t)dim * es;
+        if (it >= 2) {  // buffer b: its previous kernel must be done before H2D overwrites rel/in,
+            CUDA_TRY(cudaStreamWaitEvent(s_in, ev_k[b], 0));  // and its previous D2H before the kernel rewrites out
+        }
+        if (R > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(buf[b].rel, wbytes, (const char *)h_relation + c0 * es, pitch_h, wbytes, R,
+                                       cudaMemcpyHostToDevice, s_in));
+        if (N > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(buf[b].in, wbytes, (const char *)h_input + c0 * es, pitch_h, wbytes, N,
+                                       cudaMemcpyHostToDevice, s_in));
+        CUDA_TRY(cudaEventRecord(ev_in[b], s_in));
+        CUDA_TRY(cudaStreamWaitEvent(s_k, ev_in[b], 0));
+        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(s_k, ev_out[b], 0));
+        rc = ultra_rspmm_forward(plan, sum_op, mul_op, dtype, buf[b].rel, buf[b].in, buf[b].out, wd, buf[b].scr,
+                                 sb, s_k);
+        if (rc) break;
+        CUDA_TRY(cudaEventRecord(ev_k[b], s_k));
+        CUDA_TRY(cudaStreamWaitEvent(s_out, ev_k[b], 0));
+        if (N > 0)
+            CUDA_TRY(cudaMemcpy2DAsync((char *)h_output + c0 * es, pitch_h, buf[b].out, wbytes, wbytes, N,
+                                       cudaMemcpyDeviceToHost, s_out));
+        CUDA_TRY(cudaEventRecord(ev_out[b], s_out));
+    }
+    // join the three lanes back into the caller's stream
+    CUDA_TRY(cudaEventRecord(ev_done, s_in));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
+    CUDA_TRY(cudaEventRecord(ev_done, s_k));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
+    CUDA_TRY(cudaEventRecord(ev_done, s_out));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
+    // destroying streams/events with pending work is legal: resources are released when the work completes
+    cudaEventDestroy(ev_start); cudaEventDestroy(ev_done);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_k[b]); cudaEventDestroy(ev_out[b]); }
+    cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// rspmm_plan.h -- host-side plan object shared by rspmm_plan.cu (builder) and rspmm_api.cu (launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+namespace ultra {
+
+// One sorted view of the edge list (see rspmm_kernels.cuh for the layout contract).
+struct SegOrder {
+    int2 *meta = nullptr;      // (E)
+    int *eid = nullptr;        // (E)  plan position -> caller edge id
+    int *seg_ptr = nullptr;    // (S+1)
+    int *nonempty = nullptr;   // (#non-empty + 1)
+    int4 *items = nullptr;     // (num_items), multiple of 4
+    int4 *fix = nullptr;       // (num_fix)
+    void *w = nullptr;         // (E) weights in this order, dtype of the last set_edge_weight
+    int num_seg = 0;
+    int num_items = 0;
+    int num_fix = 0;
+    int num_slots = 0;
+};
+
+}  // namespace ultra
+
+struct ultra_rspmm_plan {
+    int64_t N = 0, E = 0, R = 0;
+    ultra::SegOrder ord[3];  // FWD (by row), BWD_IN (by col), BWD_REL (by relation)
+    int *row_of_edge = nullptr;  // (E) row of each edge in FWD order (weight_grad kernel)
+    int *w_nonunit = nullptr;    // device flag: some bound weight != 1
+    bool unit_weight = true;
+    int w_dtype = -1;
+    int input_sorted = 0;
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    size_t smem_optin = 0;
+};
+
+namespace ultra {
+void set_error(const std::string &msg);
+size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
+int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t *edge_type, int64_t N, int64_t E,
+               int64_t R, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+}  // namespace ultra

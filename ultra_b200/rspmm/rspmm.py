@@ -1,0 +1,249 @@
+"""Drop-in replacement for /root/reference/ultra/rspmm/rspmm.py (same names, signatures, defaults, errors).
+
+    generalized_rspmm(edge_index, edge_type, edge_weight, relation, input, sum="add", mul="mul")   rspmm.py:167
+    RSPMM{Add,Min,Max}{Mul,Add}Function.apply(edge_index, edge_type, edge_weight, relation, input)  rspmm.py:11-164
+    backward -> (None, None, weight_grad, relation_grad, input_grad)                               rspmm.py:33-34
+
+Underneath, instead of a pybind11 ATen extension JIT-built at import (rspmm.py:181-207), calls go through the
+C ABI of include/ultra_rspmm.h (hand-written sm_100a kernels, ctypes) with a cached graph plan.  Differences
+that are visible to a caller, all deliberate:
+  * no per-call argsort / host sync: the plan is built once per (edge_index, edge_type) tensor pair and cached;
+  * the arithmetic ALWAYS runs on the GPU.  CPU tensors are accepted (the reference dispatches on
+    input.device.type, rspmm.py:19-22) but are streamed through the GPU in column slabs; without a CUDA device
+    the call raises - there is no CPU implementation in this package;
+  * weight_grad is None instead of a zeros tensor when edge_weight does not require grad (the reference's CUDA
+    path returns zeros that autograd then discards, rspmm.cu:295,312-331).
+"""
+import ctypes
+import sys
+import threading
+
+import torch
+from torch import autograd
+
+from .. import _capi
+from ..plan import GraphPlan, plan_cache, _DTYPE_ID, _stream_ptr
+
+module = sys.modules[__name__]
+
+_tls = threading.local()
+
+
+def _skip_sorted_check():
+    return getattr(_tls, "skip_sorted_check", False)
+
+
+def _forward_check(edge_index, edge_type, edge_weight, relation, input):
+    """Restates rspmm_forward_check (/root/reference/ultra/rspmm/source/rspmm.cpp:15-28) as RuntimeErrors."""
+    def dim(t, name, pos, n):
+        if t.dim() != n:
+            raise RuntimeError("Expected %d-dimensional tensor, but got %d-dimensional tensor for argument #%d '%s'"
+                               % (n, t.dim(), pos, name))
+    dim(edge_index, "edge_index", 1, 2)
+    dim(edge_type, "edge_type", 2, 1)
+    dim(edge_weight, "edge_weight", 3, 1)
+    dim(relation, "relation", 4, 2)
+    dim(input, "input", 5, 2)
+    if edge_index.dtype != torch.int64:
+        raise RuntimeError("expected scalar type Long but found %s for argument #1 'edge_index'"
+                           % str(edge_index.dtype).replace("torch.", ""))
+    if edge_type.dtype != edge_index.dtype:
+        raise RuntimeError("Expected tensor for argument #1 'edge_index' to have the same type as tensor for "
+                           "argument #2 'edge_type'; but type %s does not equal %s"
+                           % (edge_index.dtype, edge_type.dtype))
+    if input.dtype not in _DTYPE_ID:
+        names = {torch.float16: "Half", torch.bfloat16: "BFloat16"}
+        raise RuntimeError('"rspmm_forward" not implemented for \'%s\''
+                           % names.get(input.dtype, str(input.dtype).replace("torch.", "")))
+    if not (edge_weight.dtype == relation.dtype == input.dtype):
+        raise RuntimeError("Expected tensors 'edge_weight', 'relation', 'input' to have the same type; got %s, %s, %s"
+                           % (edge_weight.dtype, relation.dtype, input.dtype))
+    if edge_index.size(0) != 2:
+        raise RuntimeError("Expected tensor to have size 2 at dimension 0, but got size %d for argument #1 "
+                           "'edge_index'" % edge_index.size(0))
+    nnz = edge_index.size(1)
+    if edge_type.size(0) != nnz:
+        raise RuntimeError("Expected tensor of size [%d], but got tensor of size [%d] for argument #2 'edge_type'"
+                           % (nnz, edge_type.size(0)))
+    if edge_weight.size(0) != nnz:
+        raise RuntimeError("Expected tensor of size [%d], but got tensor of size [%d] for argument #3 "
+                           "'edge_weight'" % (nnz, edge_weight.size(0)))
+    if relation.size(1) != input.size(1):
+        raise RuntimeError("Expected tensor to have size %d at dimension 1, but got size %d for argument #4 "
+                           "'relation'" % (input.size(1), relation.size(1)))
+    devs = {t.device for t in (edge_index, edge_type, edge_weight, relation, input)}
+    if len(devs) != 1:
+        raise RuntimeError("Expected all tensors to be on the same device, got %s" % sorted(map(str, devs)))
+
+
+def _gpu_for_host_tensors():
+    if not torch.cuda.is_available():
+        raise RuntimeError("ultra_b200.rspmm: no CUDA device - rspmm has no CPU implementation in this package "
+                           "(host tensors are staged through the GPU)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _get_plan(edge_index, edge_type, num_node, num_relation):
+    return plan_cache.get(edge_index, edge_type, num_node, num_relation)
+
+
+def _run_forward(plan, sum_id, mul_id, relation, input):
+    lib = _capi.lib()
+    output = torch.empty_like(input)
+    dim = input.size(1)
+    scratch = plan.scratch(dim, input.dtype)
+    with torch.cuda.device(input.device):
+        rc = lib.ultra_rspmm_forward(plan.handle, sum_id, mul_id, _DTYPE_ID[input.dtype], relation.data_ptr(),
+                                     input.data_ptr(), output.data_ptr(), dim, scratch.data_ptr(), scratch.numel(),
+                                     _stream_ptr(input.device))
+    _capi.check(rc, "ultra_rspmm_forward")
+    return output
+
+
+def _run_backward(plan, sum_id, mul_id, relation, input, output, output_grad, need_weight_grad, num_edge):
+    lib = _capi.lib()
+    relation_grad = torch.empty_like(relation)
+    input_grad = torch.empty_like(input)
+    weight_grad = torch.empty(num_edge, dtype=input.dtype, device=input.device) if need_weight_grad else None
+    dim = input.size(1)
+    scratch = plan.scratch(dim, input.dtype)
+    with torch.cuda.device(input.device):
+        rc = lib.ultra_rspmm_backward(plan.handle, sum_id, mul_id, _DTYPE_ID[input.dtype], relation.data_ptr(),
+                                      input.data_ptr(), output.data_ptr(), output_grad.data_ptr(),
+                                      weight_grad.data_ptr() if need_weight_grad else None,
+                                      relation_grad.data_ptr(), input_grad.data_ptr(), dim, scratch.data_ptr(),
+                                      scratch.numel(), _stream_ptr(input.device))
+    _capi.check(rc, "ultra_rspmm_backward")
+    return weight_grad, relation_grad, input_grad
+
+
+# host staging: device slab buffers are cached per (plan, dim, dtype)
+_HOST_SLAB_DIM = 512
+
+
+def _run_forward_host(plan, sum_id, mul_id, relation, input, device, slab_dim=None):
+    """CPU tensors in, CPU tensor out; column slabs pipelined H2D -> kernel -> D2H (ultra_rspmm_forward_host)."""
+    lib = _capi.lib()
+    dim = input.size(1)
+    slab = min(slab_dim or _HOST_SLAB_DIM, max(dim, 1))
+    dt = _DTYPE_ID[input.dtype]
+    output = torch.empty(input.shape, dtype=input.dtype, pin_memory=True)
+    need = lib.ultra_rspmm_host_staging_bytes(plan.handle, dim, slab, dt)
+    staging = getattr(plan, "_host_staging", None)
+    if staging is None or staging.numel() < need:
+        staging = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+        plan._host_staging = staging
+    with torch.cuda.device(device):
+        rc = lib.ultra_rspmm_forward_host(plan.handle, sum_id, mul_id, dt, relation.data_ptr(), input.data_ptr(),
+                                          output.data_ptr(), dim, slab, staging.data_ptr(), staging.numel(),
+                                          _stream_ptr(device))
+        _capi.check(rc, "ultra_rspmm_forward_host")
+        torch.cuda.current_stream(device).synchronize()  # a CPU result must be complete on return
+    return output
+
+
+class _RSPMMFunctionBase(autograd.Function):
+    """Shared body of the six reference Function classes (their bodies are identical up to the kernel name)."""
+
+    sum_name = "add"
+    mul_name = "mul"
+
+    @classmethod
+    def _ids(cls):
+        return _capi.SUM_IDS[cls.sum_name], _capi.MUL_IDS[cls.mul_name]
+
+    @staticmethod
+    def _forward_impl(cls, ctx, edge_index, edge_type, edge_weight, relation, input):
+        _forward_check(edge_index, edge_type, edge_weight, relation, input)
+        sum_id, mul_id = cls._ids()
+        host = input.device.type != "cuda"
+        if host:
+            device = _gpu_for_host_tensors()
+            d_edge_index, d_edge_type = edge_index.to(device), edge_type.to(device)
+            plan = GraphPlan(d_edge_index, d_edge_type, input.size(0), relation.size(0))
+        else:
+            device = input.device
+            plan = _get_plan(edge_index, edge_type, input.size(0), relation.size(0))
+        # rspmm.py:15-17  `assert (key.diff() >= 0).all(), "Expect sorted `edge_index`"` -- evaluated once, at
+        # plan build, instead of a device->host sync on every call
+        if not _skip_sorted_check():
+            assert plan.input_sorted, "Expect sorted `edge_index`"
+        relation_c = relation.detach().contiguous()
+        input_c = input.detach().contiguous()
+        if host:
+            plan.bind_weight(edge_weight.detach().to(device))
+            output = _run_forward_host(plan, sum_id, mul_id, relation_c, input_c, device)
+        else:
+            plan.bind_weight(edge_weight)
+            output = _run_forward(plan, sum_id, mul_id, relation_c, input_c)
+        ctx.plan = plan
+        ctx.host = host
+        ctx.num_edge = edge_index.size(1)
+        ctx.save_for_backward(edge_weight, relation, input, output)
+        return output
+
+    @staticmethod
+    def _backward_impl(cls, ctx, output_grad):
+        edge_weight, relation, input, output = ctx.saved_tensors
+        plan = ctx.plan
+        sum_id, mul_id = cls._ids()
+        need_wg = ctx.needs_input_grad[2]
+        if output_grad.shape != output.shape:
+            raise RuntimeError("Expected tensor for 'output_grad' to have the same size as 'output'")
+        if ctx.host:
+            device = plan.device
+            plan.bind_weight(edge_weight.detach().to(device))
+            res = _run_backward(plan, sum_id, mul_id, relation.detach().to(device).contiguous(),
+                                input.detach().to(device).contiguous(), output.to(device).contiguous(),
+                                output_grad.to(device).contiguous(), need_wg, ctx.num_edge)
+            weight_grad, relation_grad, input_grad = [None if r is None else r.cpu() for r in res]
+        else:
+            plan.bind_weight(edge_weight)
+            weight_grad, relation_grad, input_grad = _run_backward(
+                plan, sum_id, mul_id, relation.detach().contiguous(), input.detach().contiguous(),
+                output.contiguous(), output_grad.contiguous(), need_wg, ctx.num_edge)
+        return None, None, weight_grad, relation_grad, input_grad
+
+
+def _make_function(sum_name, mul_name):
+    name = "RSPMM%s%sFunction" % (sum_name.capitalize(), mul_name.capitalize())
+
+    def forward(ctx, edge_index, edge_type, edge_weight, relation, input):
+        return _RSPMMFunctionBase._forward_impl(cls, ctx, edge_index, edge_type, edge_weight, relation, input)
+
+    def backward(ctx, output_grad):
+        return _RSPMMFunctionBase._backward_impl(cls, ctx, output_grad)
+
+    cls = type(name, (_RSPMMFunctionBase,), {
+        "sum_name": sum_name, "mul_name": mul_name,
+        "forward": staticmethod(forward), "backward": staticmethod(backward),
+        "__doc__": "rspmm %s-%s (reference class of the same name, ultra/rspmm/rspmm.py)" % (sum_name, mul_name),
+    })
+    return cls
+
+
+RSPMMAddMulFunction = _make_function("add", "mul")   # rspmm.py:11
+RSPMMMinMulFunction = _make_function("min", "mul")   # rspmm.py:37
+RSPMMMaxMulFunction = _make_function("max", "mul")   # rspmm.py:63
+RSPMMAddAddFunction = _make_function("add", "add")   # rspmm.py:89
+RSPMMMinAddFunction = _make_function("min", "add")   # rspmm.py:115
+RSPMMMaxAddFunction = _make_function("max", "add")   # rspmm.py:141
+
+
+def generalized_rspmm(edge_index, edge_type, edge_weight, relation, input, sum="add", mul="mul"):
+    """Same contract as the reference wrapper (rspmm.py:167-178); edges may come in any order.
+
+    The reference sorts the edges on every call and hands sorted copies to Function.apply; here the (cached) plan
+    owns the sorted order, so the original tensors are passed through and no sort happens after the first call.
+    """
+    name = "RSPMM%s%sFunction" % (sum.capitalize(), mul.capitalize())
+    if not hasattr(module, name):
+        raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`"
+                         % (sum, mul))
+    Function = getattr(module, name)
+    prev = _skip_sorted_check()
+    _tls.skip_sorted_check = True
+    try:
+        return Function.apply(edge_index, edge_type, edge_weight, relation, input)
+    finally:
+        _tls.skip_sorted_check = prev
