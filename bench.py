@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- rspmm edges/s (BASELINE.json metric) on B200, with roofline, e2e and the reference CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- FB15k-237 scale entity graph (14,541 nodes, 474 relation
+rows, 544,230 edges incl. inverse edges), dim=64, 128 heads per GPU -> D = 8192 fp32 columns, distmult + sum.
+Synthetic Zipf(1.0) graph (ultra_b200.synth; no datasets / network here).  One STEP = one rspmm forward over the
+whole batch (the call GeneralizedRelationalConv.message_and_aggregate makes, /root/reference/ultra/layers.py:200).
+
+  value     : edges/s, inputs resident in HBM, plan pre-built (the reference re-sorts per call), CUDA events
+  e2e       : edges/s through ultra_b200.rspmm.generalized_rspmm with pinned HOST tensors: H2D of relation+input
+              and D2H of the output inside the timed region (pipelined column slabs in the C ABI)
+  roofline  : algorithmic bytes (edge-gather model) / measured per-call device time vs the measured
+              HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference's own CPU kernel (oracle/_ref, built from /root/reference by
+              oracle/build_ref.py) on this box's host cores
+
+N > 1: one process per GPU, heads sharded (each GPU owns 128 heads; rspmm needs no collective because columns are
+independent) -> "scaling": "weak"; value = N * E / max-over-ranks device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rspmm_edges_per_sec"
+UNIT = "edges/s"
+SCALE = "fb15k237"
+HEADS = 128
+DIM = 64
+ALPHA = 1.0
+SEED = 1234 + 2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_workload(heads, device, pin_host=False):
+    from ultra_b200.synth import synth_scale
+    ei, et, R, N = synth_scale(SCALE, alpha=ALPHA, seed=SEED)
+    D = heads * DIM
+    g = torch.Generator().manual_seed(SEED)
+    # entity stack: relation rows are per-head distinct (projection of (B,R,64), layers.py:80)
+    rel = torch.randn(R, D, generator=g)
+    x = torch.randn(N, D, generator=g)
+    w = torch.ones(ei.shape[1])
+    return dict(ei=ei, et=et, w=w, rel=rel, x=x, N=N, R=R, E=ei.shape[1], D=D)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU rspmm (oracle/_ref) on the host cores, same workload and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/rspmm_ref.so not built (needs /root/reference)"}))
+        return 0
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    wl = make_workload(HEADS, "cpu")
+    ei, et, w, rel, x = wl["ei"], wl["et"], wl["w"], wl["rel"], wl["x"]
+    fn = lambda: ref.ref_generalized_rspmm(ei, et, w, rel, x, sum="add", mul="mul")  # wrapper incl. per-call argsort
+    for _ in range(max(args.warmup, 1)):
+        fn()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    value = wl["E"] * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                         "sample": "full C2 batch (128 heads, D=8192) per step through the reference wrapper "
+                                   "(per-call argsort + rspmm_add_mul_forward_cpu), %d steps" % args.steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(wl, n_gpus):
+    return {"workload": "BASELINE configs[1]: FB15k-237-scale entity graph, rspmm add-mul forward (distmult+sum), "
+                        "dim=64, %d heads per GPU" % HEADS,
+            "num_node": wl["N"], "num_relation": wl["R"], "num_edge": wl["E"], "dim": wl["D"], "heads_per_gpu": HEADS,
+            "graph": "synthetic Zipf(alpha=%.1f) + inverse edges, seed %d" % (ALPHA, SEED),
+            "l2": "no flush: input+output are 2x476 MB per call, larger than the 126 MB L2",
+            "parallelism": "head-shard x%d (no data-path collective)" % n_gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="e2e steps (default min(steps, 10))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the rspmm product path has no CPU implementation)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from ultra_b200 import _capi
+    from ultra_b200.plan import GraphPlan, _stream_ptr
+    from ultra_b200.rspmm import generalized_rspmm
+    from ultra_b200.synth import algorithmic_bytes, compulsory_bytes
+    lib = _capi.lib()
+
+    wl = make_workload(HEADS, device)
+    N, R, E, D = wl["N"], wl["R"], wl["E"], wl["D"]
+    ei_d, et_d, w_d = wl["ei"].to(device), wl["et"].to(device), wl["w"].to(device)
+    rel_d, x_d = wl["rel"].to(device), wl["x"].to(device)
+    out_d = torch.empty_like(x_d)
+    plan = GraphPlan(ei_d, et_d, N, R)
+    plan.bind_weight(w_d)
+    scratch = plan.scratch(D, torch.float32)
+    launches_per_step = 1 + (1 if (plan.info(4) > 0 or int((torch.bincount(wl["ei"][0], minlength=N) == 0).any())) else 0)
+
+    def step():
+        rc = lib.ultra_rspmm_forward(plan.handle, 0, 0, 0, rel_d.data_ptr(), x_d.data_ptr(), out_d.data_ptr(), D,
+                                     scratch.data_ptr(), scratch.numel(), _stream_ptr(device))
+        if rc != 0:
+            raise RuntimeError(lib.ultra_rspmm_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record()
+    barrier()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * E * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: public API, pinned host tensors, H2D + D2H inside the timed region -------------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    rel_h, x_h = wl["rel"].pin_memory(), wl["x"].pin_memory()
+    ei_h, et_h, w_h = wl["ei"], wl["et"], wl["w"]
+    for _ in range(2):
+        out_h = generalized_rspmm(ei_h, et_h, w_h, rel_h, x_h, sum="add", mul="mul")
+        del out_h
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(e2e_steps):
+        out_h = generalized_rspmm(ei_h, et_h, w_h, rel_h, x_h, sum="add", mul="mul")  # returns a complete CPU tensor
+        checksum += float(out_h[0, 0])
+        del out_h
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * e2e_steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kernel_ms = sum(per_step) / len(per_step)
+        ba = algorithmic_bytes(N, E, R, D)
+        achieved = ba / (kernel_ms * 1e-3) / 1e9
+        traffic = load_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(wl, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "peak_source": peak_src,
+                         "model": "edge-gather: 4*D*(E+N+R)+12*E+4*(N+1) = %d bytes per call; duration = whole forward "
+                                  "call (tiled kernel + split-row fix-up), mean of %d CUDA-event samples on the "
+                                  "launching stream" % (ba, len(per_step)),
+                         "compulsory_bytes": compulsory_bytes(N, E, R, D),
+                         "achieved_compulsory_GBs": compulsory_bytes(N, E, R, D) / (kernel_ms * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * D * (N + R),
+                    "d2h_bytes_per_step": 4 * D * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "ultra_b200.rspmm.generalized_rspmm(pinned CPU tensors) -> ultra_rspmm_forward_host",
+                    "checksum": checksum},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(wl):
+    """Reference CPU kernel (oracle/_ref) on this box's host cores, bounded sample: full C2 batch, 1 warm-up + 3 reps."""
+    from oracle import ref
+    import oracle
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    if not ref.available():
+        # C restatement (scalar, 1 thread) on a 4-head crop, normalised to the full width
+        crop = 4 * DIM
+        sei, stt, sw, _ = oracle.sort_edges(wl["ei"].numpy(), wl["et"].numpy(), wl["w"].numpy())
+        rel, x = wl["rel"][:, :crop].contiguous().numpy(), wl["x"][:, :crop].contiguous().numpy()
+        t0 = time.perf_counter()
+        oracle.c_forward("add", "mul", sei, stt, sw, rel, x)
+        dt = (time.perf_counter() - t0) * (wl["D"] / crop)
+        return {"value": wl["E"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "C oracle, 4 of 128 heads, time scaled x32 to D=8192"}
+    ei, et, w, rel, x = wl["ei"], wl["et"], wl["w"], wl["rel"], wl["x"]
+    sei, stt, sw, _ = oracle.sort_edges(ei.numpy(), et.numpy(), w.numpy())
+    tei, ttt, tw = torch.from_numpy(sei), torch.from_numpy(stt), torch.from_numpy(sw)
+    ref.ref_forward("add", "mul", tei, ttt, tw, rel, x)
+    ts, tw_ = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ref.ref_forward("add", "mul", tei, ttt, tw, rel, x)
+        ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ref.ref_generalized_rspmm(ei, et, w, rel, x)
+        tw_.append(time.perf_counter() - t0)
+    cpu_model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    cpu_model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"value": wl["E"] / min(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": "full C2 batch (128 heads, D=8192), kernel call on pre-sorted edges, min of 3 after 1 warm-up",
+            "wrapper_value": wl["E"] / min(tw_), "kernel_ms": 1e3 * min(ts), "wrapper_ms": 1e3 * min(tw_),
+            "cpu": cpu_model, "os_cpu_count": cores}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

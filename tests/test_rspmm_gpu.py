@@ -17,9 +17,10 @@ def run_ours(sum, mul, ei, et, w, rel, x, og=None, device="cuda", weight_grad=Tr
     from ultra_b200.rspmm import generalized_rspmm
     d = torch.device(device)
     ei, et = ei.to(d), et.to(d)
-    w = w.to(d).requires_grad_(og is not None and weight_grad)
-    rel = rel.to(d).requires_grad_(og is not None)
-    x = x.to(d).requires_grad_(og is not None)
+    # detach(): fresh leaves that share storage (keeps pinned-ness for the host-tensor test)
+    w = w.to(d).detach().requires_grad_(og is not None and weight_grad)
+    rel = rel.to(d).detach().requires_grad_(og is not None)
+    x = x.to(d).detach().requires_grad_(og is not None)
     out = generalized_rspmm(ei, et, w, rel, x, sum=sum, mul=mul)
     if og is None:
         return out.detach().cpu()

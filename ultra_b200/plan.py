@@ -102,15 +102,19 @@ class PlanCache:
                 edge_type.data_ptr(), edge_type._version, tuple(edge_type.shape), edge_type.stride(),
                 str(edge_index.device), int(num_node), int(num_relation))
 
-    def get(self, edge_index, edge_type, num_node, num_relation):
-        key = self._key(edge_index, edge_type, num_node, num_relation)
+    def get(self, edge_index, edge_type, num_node, num_relation, device=None):
+        """`device` is only needed for host-resident edge tensors (their plan lives on that GPU)."""
+        key = self._key(edge_index, edge_type, num_node, num_relation) + (str(device),)
         with self._lock:
             hit = self._entries.get(key)
             if hit is not None:
                 self._entries.move_to_end(key)
                 self.hits += 1
                 return hit[0]
-        plan = GraphPlan(edge_index, edge_type, num_node, num_relation)
+        if edge_index.device.type != "cuda":
+            plan = GraphPlan(edge_index.to(device), edge_type.to(device), num_node, num_relation)
+        else:
+            plan = GraphPlan(edge_index, edge_type, num_node, num_relation)
         with self._lock:
             self.misses += 1
             self._entries[key] = (plan, edge_index, edge_type)

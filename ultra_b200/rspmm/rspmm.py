@@ -87,6 +87,16 @@ def _get_plan(edge_index, edge_type, num_node, num_relation):
     return plan_cache.get(edge_index, edge_type, num_node, num_relation)
 
 
+def _bind_host_weight(plan, edge_weight, device):
+    """Host-resident weights: upload once per (tensor, version); the device copy is kept on the plan."""
+    key = (edge_weight.data_ptr(), edge_weight._version, edge_weight.dtype, tuple(edge_weight.shape))
+    if getattr(plan, "_host_weight_key", None) != key:
+        plan._host_weight_dev = edge_weight.detach().to(device)
+        plan._host_weight_key = key
+        plan._host_weight_ref = edge_weight
+    plan.bind_weight(plan._host_weight_dev)
+
+
 def _run_forward(plan, sum_id, mul_id, relation, input):
     lib = _capi.lib()
     output = torch.empty_like(input)
@@ -159,8 +169,7 @@ class _RSPMMFunctionBase(autograd.Function):
         host = input.device.type != "cuda"
         if host:
             device = _gpu_for_host_tensors()
-            d_edge_index, d_edge_type = edge_index.to(device), edge_type.to(device)
-            plan = GraphPlan(d_edge_index, d_edge_type, input.size(0), relation.size(0))
+            plan = plan_cache.get(edge_index, edge_type, input.size(0), relation.size(0), device=device)
         else:
             device = input.device
             plan = _get_plan(edge_index, edge_type, input.size(0), relation.size(0))
@@ -171,7 +180,7 @@ class _RSPMMFunctionBase(autograd.Function):
         relation_c = relation.detach().contiguous()
         input_c = input.detach().contiguous()
         if host:
-            plan.bind_weight(edge_weight.detach().to(device))
+            _bind_host_weight(plan, edge_weight, device)
             output = _run_forward_host(plan, sum_id, mul_id, relation_c, input_c, device)
         else:
             plan.bind_weight(edge_weight)
@@ -192,7 +201,7 @@ class _RSPMMFunctionBase(autograd.Function):
             raise RuntimeError("Expected tensor for 'output_grad' to have the same size as 'output'")
         if ctx.host:
             device = plan.device
-            plan.bind_weight(edge_weight.detach().to(device))
+            _bind_host_weight(plan, edge_weight, device)
             res = _run_backward(plan, sum_id, mul_id, relation.detach().to(device).contiguous(),
                                 input.detach().to(device).contiguous(), output.to(device).contiguous(),
                                 output_grad.to(device).contiguous(), need_wg, ctx.num_edge)
