@@ -146,6 +146,9 @@ void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vecto
         }
     }
     close();
+    // A warp walks 4 consecutive items in lock-step: group items of (nearly) equal length, longest first.
+    std::stable_sort(items.begin(), items.end(),
+                     [](const int4 &a, const int4 &b) { return (a.y - a.x) > (b.y - b.x); });
     while (items.size() % kSubPerWarp) items.push_back(make_int4(0, 0, 0, -1));
     nonempty.push_back(0);  // pad: the walker prefetches nonempty[j+1]
 }
