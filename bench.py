@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="e2e steps (default min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layer", action="store_true", help="skip the NBFNet-layer / 6-layer stack timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -209,7 +210,8 @@ def main():
     plan = GraphPlan(ei_d, et_d, N, R)
     plan.bind_weight(w_d)
     scratch = plan.scratch(D, torch.float32)
-    launches_per_step = 1 + (1 if (plan.info(4) > 0 or int((torch.bincount(wl["ei"][0], minlength=N) == 0).any())) else 0)
+    has_empty = bool((torch.bincount(wl["ei"][0], minlength=N) == 0).any())
+    launches_per_step = 1 + (1 if plan.info(4) > 0 else 0) + (1 if has_empty else 0)  # tiled kernel, fold, identity fill
 
     def step():
         rc = lib.ultra_rspmm_forward(plan.handle, 0, 0, 0, rel_d.data_ptr(), x_d.data_ptr(), out_d.data_ptr(), D,
@@ -263,6 +265,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * E * e2e_steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    layer_info = None if args.no_layer else bench_layer(wl, device, world, rank)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -288,6 +291,7 @@ def main():
                     "checksum": checksum},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
+            "nbfnet_layer": layer_info,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
@@ -296,6 +300,64 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bench_layer(wl, device, world, rank):
+    """NBFNet-layer ms (second half of BASELINE.json's metric): one GeneralizedRelationalConv forward of the entity
+    stack (transposes, rspmm, boundary, Linear 128->64, LayerNorm, ReLU, shortcut; /root/reference/ultra/layers.py
+    :67-88,183-240 restated PyG-free in ultra_b200.layer) at HEADS heads per GPU, and the 6-layer Bellman-Ford stack.
+    With N > 1 the stack is also timed with the north star's per-layer all-gather of node states on a side stream."""
+    import torch.distributed as dist
+    from ultra_b200.layer import GeneralizedRelationalConv, bellmanford_entity
+    from ultra_b200.shard import OverlappedStateGather
+    N, R = wl["N"], wl["R"]
+    B, d = HEADS, DIM
+    torch.manual_seed(7)
+    ei, et = wl["ei"].to(device), wl["et"].to(device)
+    layers = [GeneralizedRelationalConv(d, d, R, d, "distmult", "sum", layer_norm=True, project_relations=True).to(device)
+              for _ in range(6)]
+    rel_repr = torch.randn(B, R, d, device=device)
+    query = torch.randn(B, d, device=device)
+    h_index = torch.randint(0, N, (B,), device=device)
+    for layer in layers:
+        layer.relation = rel_repr
+    x = torch.randn(B, N, d, device=device)
+    bd = torch.zeros(B, N, d, device=device)
+    w = torch.ones(ei.shape[1], device=device)
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        layer_ms = timeit(lambda: layers[0](x, query, bd, ei, et, (N, N), w) + x)
+        stack_ms = timeit(lambda: bellmanford_entity(layers, query, h_index, ei, et, N), reps=3, warm=1)
+        info = {"layer_ms": layer_ms, "stack6_ms": stack_ms, "heads_per_gpu": B,
+                "what": "GeneralizedRelationalConv forward (distmult+sum, layer_norm, shortcut), fp32; non-rspmm parts "
+                        "are PyTorch ops (fused epilogue is SURVEY 8f row f2)"}
+        if world > 1:
+            def stack_gather():
+                g = OverlappedStateGather(B * world)
+                bellmanford_entity(layers, query, h_index, ei, et, N, hook=g.after_layer)
+                return g.wait()
+            info["stack6_ms_with_per_layer_allgather"] = timeit(stack_gather, reps=3, warm=1)
+            info["allgather_bytes_per_layer_per_gpu"] = 4 * B * world * N * d
+    del layers, x, bd
+    torch.cuda.empty_cache()
+    return info
 
 
 def cpu_baseline(wl):

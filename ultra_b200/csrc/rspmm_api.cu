@@ -97,11 +97,17 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         }
         CUDA_TRY(cudaGetLastError());
     }
-    if (so.num_fix > 0) {
-        const int ncc = (int)((D + 32 * V - 1) / (32 * V));
-        const long long warps = (long long)so.num_fix * ncc;
+    const int ncc = (int)((D + 32 * V - 1) / (32 * V));
+    if (so.num_fix_long > 0) {
+        fold_partials_kernel<T, Nd::red><<<so.num_fix_long * ncc, 256, 0, stream>>>(so.fix, so.num_fix_long, scratch,
+                                                                                     dst, (int)D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int num_empty = so.num_fix - so.num_fix_long;
+    if (num_empty > 0) {
+        const long long warps = (long long)num_empty * ncc;
         const int blocks = (int)((warps * 32 + 255) / 256);
-        fixup_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix, so.num_fix, scratch, dst, (int)D);
+        fill_identity_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst, (int)D);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;

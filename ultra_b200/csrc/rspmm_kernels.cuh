@@ -8,8 +8,9 @@
 //
 // Data layout (all built once per graph by rspmm_plan.cu):
 //   meta[e]   int2  (a, b | last_of_segment<<31)  edges sorted by (segment, secondary key)
-//   items[k]  int4  {e_begin, e_end, j0, slot}    <= kItemEdges edges; whole segments (slot<0) or one chunk
-//                                                 of a long segment (slot>=0 -> partial[slot])
+//   items[k]  int4  {e_begin, e_end, j0, slot}    <= kItemEdges edges; whole segments (slot=-1), a single chunk of a
+//                                                 long segment (slot>=0 -> partial[slot]), or a member of a merged
+//                                                 group of 4 full chunks (j0 |= kMergedBit; leader slot>=0, followers -2)
 //   nonempty[j]     ids of non-empty segments, in order (j0 indexes it)
 //   fix[f]    int4  {segment, slot_begin, slot_count, 0}  empty segments (count 0) and long segments
 //
@@ -32,6 +33,7 @@ constexpr int kLanesPerEdge = 8;
 constexpr int kSubPerWarp = 32 / kLanesPerEdge;  // 4 items walked concurrently by one warp
 constexpr int kTileBytes = 128;
 constexpr int kItemEdges = 64;   // max edges of a whole-segment item and chunk length of a long segment
+constexpr int kMergedBit = 1 << 30;  // items[k].z flag: member of a merged group of 4 full chunks
 constexpr int kCtaThreads = 512;
 constexpr int kCtaWarps = kCtaThreads / 32;
 
@@ -160,7 +162,8 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
 
     const int4 it = __ldg(p.items + (size_t)wi * kSubPerWarp + sg);
     const int e0 = it.x, slot = it.w;
-    int j = it.z;
+    const bool merged = (it.z & kMergedBit) != 0;  // warp-uniform: 4 full chunks of ONE long segment (cut_items)
+    int j = it.z & (kMergedBit - 1);
     const int len = it.y - it.x;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
     const int minlen = __reduce_min_sync(0xffffffffu, len);
@@ -203,32 +206,35 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             if (N::out) g2[u] = ld_row<T>(out_c, (unsigned)m[u].x, row_bytes);
             if (N::inb) g3[u] = ld_row<T>(in_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
         }
+        Vec<T> rr[U];
+        if (N::rel) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
+                if (REL_SMEM) rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
+                else rr[u] = ld_row<T>(rel_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            Vec<T> r;
-            if (N::rel) {
-                // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
-                if (REL_SMEM) r = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
-                else r = ld_row<T>(rel_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
-            }
             Vec<T> nxt;
 #pragma unroll
             for (int k = 0; k < V; k++) {
                 if (MODE == FWD) {
                     // rspmm.cu:68-70   x = Bin(rel, in); y = w * x; out = Nary(out, y)
-                    T y = bin_fwd<MUL>(r.v[k], g1[u].v[k]);
+                    T y = bin_fwd<MUL>(rr[u].v[k], g1[u].v[k]);
                     if (!UNITW) y = wv[u] * y;
                     nxt.v[k] = nary_fwd<SUM>(acc.v[k], y);
                 } else if (MODE == BWD_IN) {
                     // rspmm.cu:198-209  input_grad[col] += og * dout_dy * w * dx_din ; segment = col
                     T g = g1[u].v[k];
                     if (N::out) {
-                        T y = bin_fwd<MUL>(r.v[k], self.v[k]);
+                        T y = bin_fwd<MUL>(rr[u].v[k], self.v[k]);
                         if (!UNITW) y = wv[u] * y;
                         g = g * nary_bwd<SUM>(g2[u].v[k], y);
                     }
                     if (!UNITW) g = g * wv[u];
-                    if (MUL == M_MUL) g = g * r.v[k];
+                    if (MUL == M_MUL) g = g * rr[u].v[k];
                     nxt.v[k] = acc.v[k] + g;
                 } else {
                     // rspmm.cu:198-208  relation_grad[type] += og * dout_dy * w * dx_drel ; segment = type
@@ -246,7 +252,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
 #pragma unroll
             for (int k = 0; k < V; k++) acc.v[k] = ok[u] ? nxt.v[k] : acc.v[k];
             // segment end inside a whole-segment item: emit the finished row, start the next one
-            if (m[u].y < 0 && ok[u] && slot < 0) {
+            if (m[u].y < 0 && ok[u] && slot == -1) {
                 if (st_ok) st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
 #pragma unroll
                 for (int k = 0; k < V; k++) acc.v[k] = nary_zero<N::red, T>();
@@ -260,8 +266,17 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     int i = 0;
     for (; i + U <= minlen; i += U) body(std::false_type{}, i);
     for (; i < maxlen; i += U) body(std::true_type{}, i);
-    if (slot >= 0 && len > 0 && st_ok)
+    if (merged) {  // warp-uniform: fold the 4 chunk partials (fixed tree order), the leader stores one slot
+#pragma unroll
+        for (int off = kLanesPerEdge; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < V; k++)
+                acc.v[k] = nary_fwd<N::red>(acc.v[k], __shfl_xor_sync(0xffffffffu, acc.v[k], off));
+        }
+        if (sg == 0 && st_ok) st_plain(p.partial + (size_t)slot * p.D + c0, acc);
+    } else if (slot >= 0 && st_ok) {  // single chunk of a long segment
         st_plain(p.partial + (size_t)slot * p.D + c0, acc);
+    }
 }
 
 template <typename T, int MODE, int SUM, int MUL, bool REL_SMEM>
@@ -313,10 +328,49 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fix-up: empty segments get the identity, long segments fold their chunk partials IN ORDER (deterministic).
+// fix-up, part 1: long segments fold their chunk-group partials.  One 256-thread CTA per (segment, 128-column
+// chunk): warp w folds partials w, w+8, ... in order, then warp 0 folds the 8 warp results in order -> deterministic.
 template <typename T, int RED>
-__global__ void __launch_bounds__(256) fixup_kernel(const int4 *__restrict__ fix, int num_fix,
-                                                    const T *__restrict__ partial, T *__restrict__ dst, int D) {
+__global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restrict__ fix, int num_fix_long,
+                                                            const T *__restrict__ partial, T *__restrict__ dst,
+                                                            int D) {
+    constexpr int V = VecN<T>::value;
+    __shared__ Vec<T> part[8][32];
+    const int f = blockIdx.x % num_fix_long;
+    const int cc = blockIdx.x / num_fix_long;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = cc * 32 * V + lane * V;
+    const bool ok = c0 < D;
+    const int4 fx = __ldg(fix + f);
+    Vec<T> acc;
+#pragma unroll
+    for (int k = 0; k < V; k++) acc.v[k] = nary_zero<RED, T>();
+    if (ok) {
+        const T *src = partial + (size_t)fx.y * D + c0;
+#pragma unroll 4
+        for (int s = warp; s < fx.z; s += 8) {
+            const Vec<T> x = *reinterpret_cast<const Vec<T> *>(src + (size_t)s * D);
+#pragma unroll
+            for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<RED>(acc.v[k], x.v[k]);
+        }
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && ok) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) {
+            const Vec<T> x = part[w][lane];
+#pragma unroll
+            for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<RED>(acc.v[k], x.v[k]);
+        }
+        st_stream(dst + (size_t)fx.x * D + c0, acc);
+    }
+}
+
+// fix-up, part 2: empty segments get the Nary identity (operator.cuh:53,66,79).  One warp per (segment, 128 columns).
+template <typename T, int RED>
+__global__ void __launch_bounds__(256) fill_identity_kernel(const int4 *__restrict__ fix, int num_fix,
+                                                            T *__restrict__ dst, int D) {
     constexpr int V = VecN<T>::value;
     const int ncc = (D + 32 * V - 1) / (32 * V);
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -326,18 +380,10 @@ __global__ void __launch_bounds__(256) fixup_kernel(const int4 *__restrict__ fix
     const int cc = (int)(gw / num_fix);
     const int c0 = cc * 32 * V + lane * V;
     if (c0 >= D) return;
-    const int4 fx = __ldg(fix + f);
     Vec<T> acc;
 #pragma unroll
     for (int k = 0; k < V; k++) acc.v[k] = nary_zero<RED, T>();
-    const T *src = partial + (size_t)fx.y * D + c0;
-#pragma unroll 4
-    for (int s = 0; s < fx.z; s++) {
-        const Vec<T> x = *reinterpret_cast<const Vec<T> *>(src + (size_t)s * D);
-#pragma unroll
-        for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<RED>(acc.v[k], x.v[k]);
-    }
-    st_stream(dst + (size_t)fx.x * D + c0, acc);
+    st_stream(dst + (size_t)__ldg(fix + f).x * D + c0, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ inline int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     while ((int64_t(1) << b) < n) b++;
     return b;
 }
+// whole items <= 2E/L+1; chunks <= E/L + #long with #long <= E/L
 inline int64_t max_items(int64_t E) { return 4 * ((E + kItemEdges - 1) / kItemEdges) + 8; }
 
 struct Layout {
@@ -69,7 +70,10 @@ __global__ void validate_kernel(const int64_t *__restrict__ ei, const int64_t *_
     }
 }
 
-// order 0: (row, col)   order 1: (col, row)   order 2: (type, row)
+// order 0: (row, col)   order 1: (col, row)   order 2: (type, row).
+// The secondary key matters for speed, not correctness: with every segment's edges sorted by the gathered node id,
+// all warps sweep the gathered matrix from low to high rows roughly in step, which is what gives the gathers their
+// L1/L2 temporal locality (measured: grouping by relation type instead costs +40% forward time on a uniform graph).
 __global__ void make_keys_kernel(int order, const int64_t *__restrict__ ei, const int64_t *__restrict__ et,
                                  int64_t E, int sec_bits, unsigned long long *keys, int *vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,28 +120,42 @@ __global__ void build_meta_kernel(int order, const unsigned long long *__restric
         }                                                                                      \
     } while (0)
 
-// Cut one segment-pointer array into work items (host).  Whole segments are packed greedily up to kItemEdges
-// edges; a segment longer than that becomes ceil(deg / kItemEdges) chunk items with consecutive partial slots.
+// Cut one segment-pointer array into work items (host).
+//   * whole segments are packed greedily up to kItemEdges edges per item              {e0, e1, j0,  -1}
+//   * a segment longer than kItemEdges is cut into 64-edge chunks.  Every run of 4 FULL chunks becomes a merged
+//     group walked by one warp and combined with shuffles: leader {e0, e1, j|kMergedBit, slot}, followers {.., .., j|kMergedBit, -2};
+//     the remaining (<= 3 full + 1 partial) chunks are single chunk items            {e0, e1, j,  slot}
+//   Partial slots of one segment are consecutive and in edge order (groups, then single chunks).
+// Item order: merged groups first (a multiple of 4, so a warp never mixes a group with other items), then all other
+// items longest first, so the 4 items a warp walks in lock-step have (nearly) equal lengths.
+// fix list: long segments first, then empty segments.
 void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vector<int> &nonempty,
-               std::vector<int4> &fix, int &num_slots) {
+               std::vector<int4> &fix, int &num_slots, int &num_fix_long) {
     const int S = (int)ptr.size() - 1;
+    constexpr int kGroupEdges = kItemEdges * kSubPerWarp;
+    std::vector<int4> groups, rest, fix_empty;
     items.clear(); nonempty.clear(); fix.clear();
     num_slots = 0;
     int cur_begin = -1, cur_end = -1, cur_j0 = 0;
     auto close = [&]() {
-        if (cur_begin >= 0) items.push_back(make_int4(cur_begin, cur_end, cur_j0, -1));
+        if (cur_begin >= 0) rest.push_back(make_int4(cur_begin, cur_end, cur_j0, -1));
         cur_begin = -1;
     };
     for (int s = 0; s < S; s++) {
         const int b = ptr[s], e = ptr[s + 1], deg = e - b;
-        if (deg == 0) { fix.push_back(make_int4(s, 0, 0, 0)); continue; }
+        if (deg == 0) { fix_empty.push_back(make_int4(s, 0, 0, 0)); continue; }
         const int j = (int)nonempty.size();
         nonempty.push_back(s);
         if (deg > kItemEdges) {
             close();
             const int slot0 = num_slots;
-            for (int c = b; c < e; c += kItemEdges)
-                items.push_back(make_int4(c, std::min(c + kItemEdges, e), j, num_slots++));
+            int c = b;
+            for (; c + kGroupEdges <= e; c += kGroupEdges) {
+                for (int k = 0; k < kSubPerWarp; k++)
+                    groups.push_back(make_int4(c + k * kItemEdges, c + (k + 1) * kItemEdges, j | kMergedBit, k ? -2 : num_slots));
+                num_slots++;
+            }
+            for (; c < e; c += kItemEdges) rest.push_back(make_int4(c, std::min(c + kItemEdges, e), j, num_slots++));
             fix.push_back(make_int4(s, slot0, num_slots - slot0, 0));
         } else {
             if (cur_begin >= 0 && (e - cur_begin) > kItemEdges) close();
@@ -146,10 +164,13 @@ void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vecto
         }
     }
     close();
-    // A warp walks 4 consecutive items in lock-step: group items of (nearly) equal length, longest first.
-    std::stable_sort(items.begin(), items.end(),
+    std::stable_sort(rest.begin(), rest.end(),
                      [](const int4 &a, const int4 &b) { return (a.y - a.x) > (b.y - b.x); });
+    items = groups;
+    items.insert(items.end(), rest.begin(), rest.end());
     while (items.size() % kSubPerWarp) items.push_back(make_int4(0, 0, 0, -1));
+    num_fix_long = (int)fix.size();
+    fix.insert(fix.end(), fix_empty.begin(), fix_empty.end());
     nonempty.push_back(0);  // pad: the walker prefetches nonempty[j+1]
 }
 
@@ -159,8 +180,8 @@ size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layou
 
 int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t *edge_type, int64_t N, int64_t E,
                int64_t R, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-    if (N < 0 || E < 0 || R < 0 || N >= (int64_t(1) << 31) || E >= (int64_t(1) << 31) - 64 ||
-        R >= (int64_t(1) << 31)) {
+    if (N < 0 || E < 0 || R < 0 || N >= (int64_t(1) << 30) || E >= (int64_t(1) << 31) - 64 ||
+        R >= (int64_t(1) << 24)) {
         set_error("plan_build: num_node / num_edge / num_relation out of int32 range");
         return 1;
     }
@@ -253,7 +274,7 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         h_ptr.resize((size_t)S[o] + 1);
         CUDA_TRY(cudaMemcpyAsync(h_ptr.data(), so.seg_ptr, (size_t)(S[o] + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        cut_items(h_ptr, items, nonempty, fix, so.num_slots);
+        cut_items(h_ptr, items, nonempty, fix, so.num_slots, so.num_fix_long);
         if ((int64_t)items.size() > max_items(E)) {
             delete plan;
             set_error("plan_build: item bound exceeded");

@@ -20,6 +20,7 @@ struct SegOrder {
     int num_seg = 0;
     int num_items = 0;
     int num_fix = 0;
+    int num_fix_long = 0;      // fix[0 .. num_fix_long) are long segments, the rest are empty segments
     int num_slots = 0;
 };
 

@@ -1,0 +1,123 @@
+"""PyG-free restatement of the ONE caller of the hot path: GeneralizedRelationalConv's fused route
+(/root/reference/ultra/layers.py:67-88 forward, :183-231 message_and_aggregate, :233-240 update).
+
+The reference class is a torch_geometric MessagePassing subclass; PyG is not part of this environment and the layer
+is outside the rspmm contract, so this module exists for two things only: measuring "NBFNet-layer ms"
+(BASELINE.json metric) and layer-level parity tests.  Parameter names match the reference so its checkpoints'
+state-dict keys (`linear`, `layer_norm`, `relation`, `relation_linear`, `relation_projection.{0,2}`) load unchanged.
+Only the fused path is restated: `rotate` messages and the PyG unfused fallback (layers.py:91-94,135-181) are not.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .rspmm import generalized_rspmm
+
+
+class GeneralizedRelationalConv(nn.Module):
+    eps = 1e-6
+    message2mul = {"transe": "add", "distmult": "mul"}  # layers.py:16-19
+
+    def __init__(self, input_dim, output_dim, num_relation, query_input_dim, message_func="distmult",
+                 aggregate_func="pna", layer_norm=False, activation="relu", dependent=False,
+                 project_relations=False):
+        super().__init__()
+        self.input_dim, self.output_dim = input_dim, output_dim
+        self.num_relation, self.query_input_dim = num_relation, query_input_dim
+        self.message_func, self.aggregate_func = message_func, aggregate_func
+        self.dependent, self.project_relations = dependent, project_relations
+        self.layer_norm = nn.LayerNorm(output_dim) if layer_norm else None
+        self.activation = getattr(F, activation) if isinstance(activation, str) else activation
+        self.linear = nn.Linear(input_dim * (13 if aggregate_func == "pna" else 2), output_dim)  # layers.py:44-47
+        if dependent:
+            self.relation_linear = nn.Linear(query_input_dim, num_relation * input_dim)
+        elif not project_relations:
+            self.relation = nn.Embedding(num_relation, input_dim)
+        else:
+            self.relation = None  # set by the caller after the relation-graph pass (models.py:184-185)
+            self.relation_projection = nn.Sequential(nn.Linear(input_dim, input_dim), nn.ReLU(),
+                                                     nn.Linear(input_dim, input_dim))
+
+    def forward(self, input, query, boundary, edge_index, edge_type, size, edge_weight=None):
+        """input, boundary: (B, N, d); query: (B, d_q); returns (B, N, output_dim).  layers.py:67-88."""
+        batch_size = len(query)
+        if self.dependent:
+            relation = self.relation_linear(query).view(batch_size, self.num_relation, self.input_dim)
+        elif not self.project_relations:
+            relation = self.relation.weight.expand(batch_size, -1, -1)
+        else:
+            relation = self.relation_projection(self.relation)
+        if edge_weight is None:
+            edge_weight = torch.ones(len(edge_type), device=input.device, dtype=input.dtype)
+        if self.message_func not in self.message2mul:
+            raise ValueError("Unknown message function `%s`" % self.message_func)
+        update = self.message_and_aggregate(edge_index, input, relation, boundary, edge_type, edge_weight, size[0])
+        return self.update(update, input)
+
+    def message_and_aggregate(self, edge_index, input, relation, boundary, edge_type, edge_weight, dim_size):
+        """layers.py:183-231: (B,N,d) -> (N,B*d) copies, rspmm, boundary as the self-loop message."""
+        batch_size, num_node = input.shape[:2]
+        input = input.transpose(0, 1).flatten(1)
+        relation = relation.transpose(0, 1).flatten(1)
+        boundary = boundary.transpose(0, 1).flatten(1)
+        mul = self.message2mul[self.message_func]
+        rspmm = lambda rel, x, s: generalized_rspmm(edge_index, edge_type, edge_weight, rel, x, sum=s, mul=mul)
+        if self.aggregate_func == "sum":
+            update = rspmm(relation, input, "add") + boundary
+        elif self.aggregate_func == "mean":
+            update = (rspmm(relation, input, "add") + boundary) / self._degree_out(edge_index, dim_size, input)
+        elif self.aggregate_func == "max":
+            update = torch.max(rspmm(relation, input, "max"), boundary)
+        elif self.aggregate_func == "pna":  # layers.py:208-226
+            degree_out = self._degree_out(edge_index, dim_size, input)
+            sum_ = rspmm(relation, input, "add")
+            sq_sum = rspmm(relation ** 2, input ** 2, "add")
+            max_ = torch.max(rspmm(relation, input, "max"), boundary)
+            min_ = torch.min(rspmm(relation, input, "min"), boundary)
+            mean = (sum_ + boundary) / degree_out
+            sq_mean = (sq_sum + boundary ** 2) / degree_out
+            std = (sq_mean - mean ** 2).clamp(min=self.eps).sqrt()
+            features = torch.cat([mean.unsqueeze(-1), max_.unsqueeze(-1), min_.unsqueeze(-1), std.unsqueeze(-1)],
+                                 dim=-1).flatten(-2)
+            scale = degree_out.log()
+            scale = scale / scale.mean()
+            scales = torch.cat([torch.ones_like(scale), scale, 1 / scale.clamp(min=1e-2)], dim=-1)
+            update = (features.unsqueeze(-1) * scales.unsqueeze(-2)).flatten(-2)
+        else:
+            raise ValueError("Unknown aggregation function `%s`" % self.aggregate_func)
+        return update.view(num_node, batch_size, -1).transpose(0, 1)
+
+    @staticmethod
+    def _degree_out(edge_index, dim_size, like):
+        # PyG `degree(index, dim_size)` with index = edge_index[1] (flow source_to_target), +1 for the self loop
+        deg = torch.bincount(edge_index[1], minlength=dim_size).to(like.dtype)
+        return deg.unsqueeze(-1) + 1
+
+    def update(self, update, input):  # layers.py:233-240
+        output = self.linear(torch.cat([input, update], dim=-1))
+        if self.layer_norm is not None:
+            output = self.layer_norm(output)
+        if self.activation:
+            output = self.activation(output)
+        return output
+
+
+def bellmanford_entity(layers, query, h_index, edge_index, edge_type, num_node, short_cut=True, hook=None):
+    """Entity-graph Bellman-Ford loop of EntityNBFNet.bellmanford (/root/reference/ultra/models.py:131-175) over a
+    list of GeneralizedRelationalConv layers whose `.relation` is already set.  query: (B, d), h_index: (B,).
+    `hook(layer_idx, hidden)` is called after every layer (used by the head-sharded runner to launch all-gathers)."""
+    batch_size = len(h_index)
+    boundary = torch.zeros(batch_size, num_node, query.shape[-1], device=query.device, dtype=query.dtype)
+    index = h_index.unsqueeze(-1).expand_as(query)
+    boundary.scatter_add_(1, index.unsqueeze(1), query.unsqueeze(1))
+    edge_weight = torch.ones(edge_index.shape[1], device=query.device, dtype=query.dtype)
+    size = (num_node, num_node)
+    layer_input = boundary
+    for li, layer in enumerate(layers):
+        hidden = layer(layer_input, query, boundary, edge_index, edge_type, size, edge_weight)
+        if short_cut and hidden.shape == layer_input.shape:
+            hidden = hidden + layer_input
+        if hook is not None:
+            hook(li, hidden)
+        layer_input = hidden
+    return layer_input
