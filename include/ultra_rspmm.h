@@ -104,6 +104,24 @@ int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, i
                          size_t scratch_bytes, void *stream);
 
 /*
+ * Head-major variants: the NBFNet layer keeps its state as (num_heads, rows, head_dim) = (B, N, d); the reference
+ * transposes it into (N, B*d) copies before every rspmm call and back afterwards
+ * (/root/reference/ultra/layers.py:190-192,230).  These entry points read and write the (B, rows, d) layout
+ * directly - relation (B, R, d), input/output/output_grad/input_grad (B, N, d), relation_grad (B, R, d) - and can
+ * fold the layer's boundary term (the self-loop message, layers.py:199-207) into the store:
+ *     output = Nary(rspmm(...), boundary)    i.e. + for sum, max / min for max / min;   boundary may be NULL.
+ * Requirements: head_dim * sizeof(dtype) is a multiple of 128 bytes, pointers 16-byte aligned.  For min/max the
+ * `output` handed to backward_heads is the (boundary-folded) forward output.  weight_grad is not offered here.
+ */
+int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                              const void *input, const void *boundary, void *output, int64_t num_heads,
+                              int64_t head_dim, void *scratch, size_t scratch_bytes, void *stream);
+int ultra_rspmm_backward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                               const void *input, const void *output, const void *output_grad, void *relation_grad,
+                               void *input_grad, int64_t num_heads, int64_t head_dim, void *scratch,
+                               size_t scratch_bytes, void *stream);
+
+/*
  * End-to-end forward from HOST buffers (pinned for full speed): relation/input/output live in host memory;
  * the call pipelines column slabs  H2D copy -> kernel -> D2H copy  on three internal streams forked from and
  * joined back to `stream`.  `staging` is a caller-provided device buffer; ultra_rspmm_host_staging_bytes()
@@ -114,6 +132,20 @@ size_t ultra_rspmm_host_staging_bytes(const ultra_rspmm_plan *plan, int64_t dim,
 int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype,
                              const void *h_relation, const void *h_input, void *h_output, int64_t dim,
                              int64_t slab_dim, void *staging, size_t staging_bytes, void *stream);
+
+/*
+ * Fused NBFNet layer epilogue, fp32:
+ *     out[m,:] = (shortcut ? x[m,:] : 0) + act( LN( weight . [x[m,:] ; u[m,:]] + bias ) )
+ * replaces GeneralizedRelationalConv.update (/root/reference/ultra/layers.py:233-240: cat, Linear(128->64), LayerNorm,
+ * ReLU) and the residual add of the Bellman-Ford loop (/root/reference/ultra/models.py:158-160).
+ *   x, u, out : device (num_rows, 64) row-major, num_rows = heads * nodes (the (B, N, 64) layer state as is)
+ *   weight_t  : device (128, 64) = nn.Linear.weight transposed;  bias / ln_gamma / ln_beta : device (64) or NULL
+ * Only in_dim == 128, out_dim == 64 is implemented (sum / mean / max aggregation at ULTRA's dim 64); anything else
+ * returns an error and the caller keeps its own epilogue.
+ */
+int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_t, const float *bias,
+                            const float *ln_gamma, const float *ln_beta, float *out, int64_t num_rows, int64_t in_dim,
+                            int64_t out_dim, float ln_eps, int layer_norm, int relu, int shortcut, void *stream);
 
 #ifdef __cplusplus
 }

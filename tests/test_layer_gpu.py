@@ -104,3 +104,114 @@ def test_bellmanford_stack_head_sharding_is_exact(cuda_device):
                 layer.relation = shard_heads(rel_repr, rank, 2)
             part = bellmanford_entity(layers, shard_heads(query, rank, 2), shard_heads(h_index, rank, 2), ei, et, N)
             torch.testing.assert_close(part, shard_heads(full, rank, 2), rtol=1e-5, atol=1e-5)
+
+
+# ---- head-major kernels and the fused epilogue -------------------------------------------------
+@pytest.mark.parametrize("sum,mul", [("add", "mul"), ("add", "add"), ("max", "mul"), ("min", "add")])
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.float32, 32), (torch.float64, 16)])
+@pytest.mark.parametrize("with_boundary", [True, False])
+def test_rspmm_heads_equals_flat_path(cuda_device, sum, mul, dtype, d, with_boundary):
+    """(B, N, d) in / out without transposes must be BIT-identical to transpose -> generalized_rspmm -> (+boundary)
+    -> transpose back (layers.py:190-207,230), forward and backward."""
+    from ultra_b200.fused import rspmm_heads
+    from ultra_b200.rspmm import generalized_rspmm
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    B, N, R, E = 5, 90, 7, 2500
+    ei = torch.randint(0, N - 3, (2, E), generator=g)
+    ei[0, :700] = 4  # a long row
+    et = torch.randint(0, R, (E,), generator=g)
+    w = (torch.rand(E, generator=g, dtype=dtype) + 0.5)
+    rel = torch.randn(B, R, d, generator=g, dtype=dtype)
+    x = torch.randn(B, N, d, generator=g, dtype=dtype)
+    bd = torch.randn(B, N, d, generator=g, dtype=dtype)
+    og = torch.randn(B, N, d, generator=g, dtype=dtype)
+    ei, et, w = ei.to(dev), et.to(dev), w.to(dev)
+
+    def leaves():
+        return [t.to(dev).clone().requires_grad_() for t in (rel, x, bd)]
+    r1, x1, b1 = leaves()
+    out = rspmm_heads(ei, et, w, r1, x1, b1 if with_boundary else None, sum=sum, mul=mul)
+    out.backward(og.to(dev))
+    r2, x2, b2 = leaves()
+    flat = generalized_rspmm(ei, et, w, r2.transpose(0, 1).flatten(1), x2.transpose(0, 1).flatten(1), sum=sum, mul=mul)
+    if with_boundary:
+        bf = b2.transpose(0, 1).flatten(1)
+        flat = flat + bf if sum == "add" else (torch.max(flat, bf) if sum == "max" else torch.min(flat, bf))
+    ref = flat.view(N, B, d).transpose(0, 1)
+    ref.backward(og.to(dev))
+    assert torch.equal(out, ref)
+    assert torch.equal(x1.grad, x2.grad)
+    assert torch.equal(r1.grad, r2.grad)
+    if with_boundary and sum == "add":
+        assert torch.equal(b1.grad, b2.grad)
+
+
+@pytest.mark.parametrize("layer_norm,relu,shortcut", [(True, True, True), (True, True, False), (False, True, True),
+                                                      (True, False, False)])
+def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut):
+    from ultra_b200.fused import nbfnet_update
+    dev = cuda_device
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(128, 64).to(dev)
+    ln = torch.nn.LayerNorm(64).to(dev) if layer_norm else None
+    if ln is not None:
+        with torch.no_grad():
+            ln.weight.uniform_(0.5, 1.5)
+            ln.bias.uniform_(-0.5, 0.5)
+    for M in (1, 127, 128, 1000, 128 * 300 + 17):
+        x, u = torch.randn(M, 64, device=dev), torch.randn(M, 64, device=dev) * 3
+        with torch.no_grad():
+            got = nbfnet_update(x, u, lin, ln, relu=relu, shortcut=shortcut)
+            ref = lin(torch.cat([x, u], -1).double().float())
+            ref = torch.nn.functional.linear(torch.cat([x, u], -1).double(), lin.weight.double(), lin.bias.double())
+            if ln is not None:
+                ref = torch.nn.functional.layer_norm(ref, (64,), ln.weight.double(), ln.bias.double(), ln.eps)
+            if relu:
+                ref = torch.relu(ref)
+            if shortcut:
+                ref = ref + x.double()
+        torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("message,aggregate", [("distmult", "sum"), ("transe", "max"), ("distmult", "mean")])
+def test_fused_layer_matches_restatement(cuda_device, message, aggregate):
+    """Fast path (head-major rspmm + one-kernel epilogue) against the literal restatement (fuse=False)."""
+    from ultra_b200.layer import GeneralizedRelationalConv, bellmanford_entity
+    torch.manual_seed(2)
+    dev = cuda_device
+    B, N, R, d, E = 6, 300, 9, 64, 4000
+    layers = [GeneralizedRelationalConv(d, d, R, d, message, aggregate, layer_norm=True, project_relations=True).to(dev)
+              for _ in range(3)]
+    rel_repr = torch.randn(B, R, d, device=dev)
+    for layer in layers:
+        layer.relation = rel_repr
+    query = torch.randn(B, d, device=dev)
+    h_index = torch.randint(0, N, (B,), device=dev)
+    ei = torch.randint(0, N, (2, E), device=dev)
+    et = torch.randint(0, R, (E,), device=dev)
+    try:
+        with torch.no_grad():
+            fast = bellmanford_entity(layers, query, h_index, ei, et, N)
+            GeneralizedRelationalConv.fuse = False
+            slow = bellmanford_entity(layers, query, h_index, ei, et, N)
+        torch.testing.assert_close(fast, slow, rtol=1e-4, atol=1e-4)
+        # training mode: head-major rspmm under autograd + PyTorch epilogue
+        GeneralizedRelationalConv.fuse = True
+        q1 = query.clone().requires_grad_()
+        out1 = bellmanford_entity(layers, q1, h_index, ei, et, N)
+        out1.square().mean().backward()
+        g_fast = [p.grad.clone() for p in layers[0].parameters() if p.grad is not None]
+        for layer in layers:
+            layer.zero_grad()
+        GeneralizedRelationalConv.fuse = False
+        q2 = query.clone().requires_grad_()
+        out2 = bellmanford_entity(layers, q2, h_index, ei, et, N)
+        out2.square().mean().backward()
+        g_slow = [p.grad.clone() for p in layers[0].parameters() if p.grad is not None]
+        torch.testing.assert_close(out1, out2, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(q1.grad, q2.grad, rtol=1e-3, atol=1e-5)
+        for a, b in zip(g_fast, g_slow):
+            torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
+    finally:
+        GeneralizedRelationalConv.fuse = True

@@ -35,15 +35,43 @@ template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *>
 }
 
 // ---- one segment pass (tiled kernel + fix-up, or the generic kernel) -------------------------------------
+// heads == 0: flat (rows, D) matrices.  heads > 0: head-major (heads, rows, D / heads) matrices.
 template <typename T, int MODE, int SUM, int MUL>
 int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input, const T *output,
-                const T *outgrad, T *dst, T *scratch, int64_t D, cudaStream_t stream) {
+                const T *outgrad, T *dst, T *scratch, int64_t D, cudaStream_t stream, int64_t heads = 0,
+                const T *boundary = nullptr) {
     using Nd = Needs<MODE, SUM, MUL>;
     const SegOrder &so = plan->ord[MODE];
     const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
     if (so.num_seg == 0 || D == 0) return 0;
 
-    if (!vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch})) {
+    constexpr int V = VecN<T>::value;
+    constexpr int TILE = kLanesPerEdge * V;
+    Layout lay;
+    if (heads > 0) {
+        const int64_t d = D / heads;
+        if (d * heads != D || (d * (int64_t)sizeof(T)) % kTileBytes != 0 ||
+            !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary})) {
+            set_error("head-major layout needs head_dim * sizeof(T) to be a multiple of 128 bytes and 16-byte "
+                      "aligned pointers");
+            return 1;
+        }
+        lay.tpg = (int)(d * sizeof(T) / kTileBytes);
+        lay.group_cols = (int)d;
+        lay.row_bytes = (unsigned)(d * sizeof(T));
+        lay.grp_node_bytes = (long long)plan->N * lay.row_bytes;
+        lay.grp_rel_bytes = (long long)plan->R * lay.row_bytes;
+    } else {
+        lay.tpg = (int)((D + TILE - 1) / TILE);
+        lay.group_cols = (int)D;
+        lay.row_bytes = (unsigned)(D * sizeof(T));
+        lay.grp_node_bytes = 0;
+        lay.grp_rel_bytes = 0;
+    }
+    const long long dst_grp_bytes = MODE == BWD_REL ? lay.grp_rel_bytes : lay.grp_node_bytes;
+
+    if (heads == 0 && !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary})) {
+        if (boundary != nullptr) { set_error("boundary fusion needs the vector path (D % 4 == 0, aligned)"); return 1; }
         const long long total = (long long)so.num_seg * D;
         const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)plan->sm_count * 16);
         seg_reduce_generic_kernel<T, MODE, SUM, MUL><<<blocks, 256, 0, stream>>>(
@@ -52,13 +80,11 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         return 0;
     }
 
-    constexpr int V = VecN<T>::value;
-    constexpr int TILE = kLanesPerEdge * V;
     SegParams<T> p;
     p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.nonempty = so.nonempty; p.items = so.items;
     p.num_warp_items = so.num_items / kSubPerWarp;
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
-    p.dst = dst; p.partial = scratch;
+    p.dst = dst; p.partial = scratch; p.boundary = boundary; p.lay = lay;
     p.D = (int)D; p.R = (int)plan->R;
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
@@ -99,15 +125,16 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     }
     const int ncc = (int)((D + 32 * V - 1) / (32 * V));
     if (so.num_fix_long > 0) {
-        fold_partials_kernel<T, Nd::red><<<so.num_fix_long * ncc, 256, 0, stream>>>(so.fix, so.num_fix_long, scratch,
-                                                                                     dst, (int)D);
+        fold_partials_kernel<T, Nd::red><<<so.num_fix_long * ncc, 256, 0, stream>>>(
+            so.fix, so.num_fix_long, scratch, dst, boundary, (int)D, lay, dst_grp_bytes);
         CUDA_TRY(cudaGetLastError());
     }
     const int num_empty = so.num_fix - so.num_fix_long;
     if (num_empty > 0) {
         const long long warps = (long long)num_empty * ncc;
         const int blocks = (int)((warps * 32 + 255) / 256);
-        fill_identity_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst, (int)D);
+        fill_identity_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst, boundary,
+                                                                     (int)D, lay, dst_grp_bytes);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -115,21 +142,22 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
 
 template <typename T, int SUM, int MUL>
 int forward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, void *output, int64_t D,
-              void *scratch, cudaStream_t stream) {
+              void *scratch, cudaStream_t stream, int64_t heads = 0, const void *boundary = nullptr) {
     return launch_pass<T, FWD, SUM, MUL>(plan, (const T *)relation, (const T *)input, nullptr, nullptr, (T *)output,
-                                         (T *)scratch, D, stream);
+                                         (T *)scratch, D, stream, heads, (const T *)boundary);
 }
 
 template <typename T, int SUM, int MUL>
 int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, const void *output,
                const void *outgrad, void *wgrad, void *rgrad, void *igrad, int64_t D, void *scratch,
-               cudaStream_t stream) {
+               cudaStream_t stream, int64_t heads = 0) {
     int rc = launch_pass<T, BWD_IN, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
-                                              (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream);
+                                              (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads);
     if (rc) return rc;
     rc = launch_pass<T, BWD_REL, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
-                                           (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream);
+                                           (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream, heads);
     if (rc) return rc;
+    if (wgrad != nullptr && heads > 0) { set_error("weight_grad is not available in the head-major layout"); return 1; }
     if (wgrad != nullptr && plan->E > 0) {
         const SegOrder &so = plan->ord[FWD];
         const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
@@ -266,6 +294,41 @@ int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, i
     } else {
         DISPATCH_OPS(backward_t, double, plan, relation, input, output, output_grad, weight_grad, relation_grad,
                      input_grad, dim, scratch, stream)
+    }
+    return 1;
+}
+
+int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                              const void *input, const void *boundary, void *output, int64_t num_heads,
+                              int64_t head_dim, void *scratch, size_t scratch_bytes_, void *stream_) {
+    if (num_heads <= 0 || head_dim <= 0) { set_error("forward_heads: num_heads / head_dim must be positive"); return 1; }
+    const int64_t dim = num_heads * head_dim;
+    if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
+    if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("forward_heads: scratch too small"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype == ULTRA_RSPMM_F32) {
+        DISPATCH_OPS(forward_t, float, plan, relation, input, output, dim, scratch, stream, num_heads, boundary)
+    } else {
+        DISPATCH_OPS(forward_t, double, plan, relation, input, output, dim, scratch, stream, num_heads, boundary)
+    }
+    return 1;
+}
+
+int ultra_rspmm_backward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
+                               const void *input, const void *output, const void *output_grad, void *relation_grad,
+                               void *input_grad, int64_t num_heads, int64_t head_dim, void *scratch,
+                               size_t scratch_bytes_, void *stream_) {
+    if (num_heads <= 0 || head_dim <= 0) { set_error("backward_heads: num_heads / head_dim must be positive"); return 1; }
+    const int64_t dim = num_heads * head_dim;
+    if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
+    if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("backward_heads: scratch too small"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype == ULTRA_RSPMM_F32) {
+        DISPATCH_OPS(backward_t, float, plan, relation, input, output, output_grad, nullptr, relation_grad, input_grad,
+                     dim, scratch, stream, num_heads)
+    } else {
+        DISPATCH_OPS(backward_t, double, plan, relation, input, output, output_grad, nullptr, relation_grad,
+                     input_grad, dim, scratch, stream, num_heads)
     }
     return 1;
 }

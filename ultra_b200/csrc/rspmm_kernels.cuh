@@ -94,6 +94,19 @@ template <int SUM, typename T> __device__ __forceinline__ T nary_bwd(T r, T x) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Feature-matrix layout.  A 128-byte column tile t of row r lives at
+//     base + (t / tpg) * grp_bytes(rows) + r * row_bytes + (t % tpg) * 128
+//   flat  (rows, D)      : tpg = #tiles, row_bytes = D * sizeof(T)                (the reference's rspmm layout)
+//   heads (B, rows, d)   : tpg = d * sizeof(T) / 128, row_bytes = d * sizeof(T), grp_bytes = rows * row_bytes
+//                          (the NBFNet layer's native layout: no transpose copies, ultra/layers.py:190-192)
+struct Layout {
+    int tpg;                     // tiles per group (head)
+    int group_cols;              // columns per group (D flat, d heads) - ragged last tile check
+    unsigned row_bytes;
+    long long grp_node_bytes;    // group stride of the N-row matrices (input, output, outgrad, boundary, input_grad)
+    long long grp_rel_bytes;     // group stride of the R-row matrices (relation, relation_grad)
+};
+
 template <typename T> struct SegParams {
     const int2 *meta;
     const T *w;  // per-edge weight in this order, or nullptr = all ones
@@ -106,7 +119,9 @@ template <typename T> struct SegParams {
     const T *output;    // (N, D)   backward only
     const T *outgrad;   // (N, D)   backward only
     T *dst;             // output / input_grad / relation_grad
-    T *partial;         // (num_slots, D)
+    T *partial;         // (num_slots, D), always flat
+    const T *boundary;  // forward only, optional: out = Nary(agg, boundary) (the NBFNet self-loop message); dst layout
+    Layout lay;         // where tile t / row r of the feature matrices live (flat (rows, D) or head-major (B, rows, d))
     int D;
     int R;
     int num_tiles;
@@ -154,11 +169,14 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const int lane = threadIdx.x & 31;
     const int q = lane & (kLanesPerEdge - 1);
     const int sg = lane >> 3;
-    int c0 = tile * TILE + q * V;
-    const bool st_ok = c0 < p.D;   // lanes past the last column of a ragged tile compute on column 0, never store
-    if (!st_ok) c0 = 0;
-    const unsigned row_bytes = (unsigned)p.D * (unsigned)sizeof(T);
-    const size_t c0_bytes = (size_t)c0 * sizeof(T);
+    const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
+    int cin = tin * TILE + q * V;  // column inside the group
+    const bool st_ok = cin < p.lay.group_cols;  // lanes past a ragged last tile compute on column 0, never store
+    if (!st_ok) cin = 0;
+    const int c0 = grp * p.lay.group_cols + cin;  // global column (flat partial buffer)
+    const unsigned row_bytes = p.lay.row_bytes;
+    const size_t off_n = (size_t)grp * p.lay.grp_node_bytes + (size_t)cin * sizeof(T);
+    const size_t off_r = (size_t)grp * p.lay.grp_rel_bytes + (size_t)cin * sizeof(T);
 
     const int4 it = __ldg(p.items + (size_t)wi * kSubPerWarp + sg);
     const int e0 = it.x, slot = it.w;
@@ -172,12 +190,14 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
 
     const int2 *mp = p.meta + e0;
     const T *wp = UNITW ? nullptr : p.w + e0;
-    const char *g1_c = reinterpret_cast<const char *>(MODE == FWD ? p.input : p.outgrad) + c0_bytes;
-    const char *out_c = reinterpret_cast<const char *>(p.output) + c0_bytes;
-    const char *in_c = reinterpret_cast<const char *>(p.input) + c0_bytes;
-    const char *rel_c = reinterpret_cast<const char *>(p.relation) + c0_bytes;
+    const char *g1_c = reinterpret_cast<const char *>(MODE == FWD ? p.input : p.outgrad) + off_n;
+    const char *out_c = reinterpret_cast<const char *>(p.output) + off_n;
+    const char *in_c = reinterpret_cast<const char *>(p.input) + off_n;
+    const char *rel_c = reinterpret_cast<const char *>(p.relation) + off_r;
     const char *self_c = (MODE == BWD_IN) ? in_c : rel_c;
-    char *dst_c = reinterpret_cast<char *>(p.dst) + c0_bytes;
+    char *dst_c = reinterpret_cast<char *>(p.dst) + (MODE == BWD_REL ? off_r : off_n);
+    const char *bnd_c = reinterpret_cast<const char *>(p.boundary) + off_n;
+    const bool has_bnd = (MODE == FWD) && p.boundary != nullptr;
     const uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;
 
     Vec<T> acc, self;
@@ -253,7 +273,14 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             for (int k = 0; k < V; k++) acc.v[k] = ok[u] ? nxt.v[k] : acc.v[k];
             // segment end inside a whole-segment item: emit the finished row, start the next one
             if (m[u].y < 0 && ok[u] && slot == -1) {
-                if (st_ok) st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
+                if (st_ok) {
+                    if (has_bnd) {
+                        const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
+#pragma unroll
+                        for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<N::red>(acc.v[k], bv.v[k]);
+                    }
+                    st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
+                }
 #pragma unroll
                 for (int k = 0; k < V; k++) acc.v[k] = nary_zero<N::red, T>();
                 j++;
@@ -308,11 +335,15 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
                 const int nvec = p.R * kLanesPerEdge;
                 for (int idx = threadIdx.x; idx < nvec; idx += kCtaThreads) {
                     const int r = idx >> 3, qq = idx & 7;
-                    const int c = tile * TILE + qq * V;
+                    const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
+                    const int cin = tin * TILE + qq * V;
                     Vec<T> x;
 #pragma unroll
                     for (int k = 0; k < V; k++) x.v[k] = T(0);
-                    if (c < p.D) x = ld_gather(p.relation + (size_t)r * p.D + c);
+                    if (cin < p.lay.group_cols)
+                        x = ld_gather(reinterpret_cast<const T *>(
+                            reinterpret_cast<const char *>(p.relation) + (size_t)grp * p.lay.grp_rel_bytes +
+                            (size_t)r * p.lay.row_bytes + (size_t)cin * sizeof(T)));
                     *reinterpret_cast<Vec<T> *>(rel_s + r * TILE + qq * V) = x;
                 }
                 __syncthreads();
@@ -328,12 +359,20 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// byte offset of (row `seg`, global column c0) in a matrix with layout `lay` and group stride grp_bytes
+template <typename T>
+__device__ __forceinline__ size_t dst_offset(const Layout &lay, long long grp_bytes, int c0, int seg) {
+    const int grp = c0 / lay.group_cols, cin = c0 - grp * lay.group_cols;
+    return (size_t)grp * grp_bytes + (size_t)seg * lay.row_bytes + (size_t)cin * sizeof(T);
+}
+
 // fix-up, part 1: long segments fold their chunk-group partials.  One 256-thread CTA per (segment, 128-column
 // chunk): warp w folds partials w, w+8, ... in order, then warp 0 folds the 8 warp results in order -> deterministic.
 template <typename T, int RED>
 __global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restrict__ fix, int num_fix_long,
                                                             const T *__restrict__ partial, T *__restrict__ dst,
-                                                            int D) {
+                                                            const T *__restrict__ boundary, int D, Layout lay,
+                                                            long long grp_bytes) {
     constexpr int V = VecN<T>::value;
     __shared__ Vec<T> part[8][32];
     const int f = blockIdx.x % num_fix_long;
@@ -363,14 +402,21 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restri
 #pragma unroll
             for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<RED>(acc.v[k], x.v[k]);
         }
-        st_stream(dst + (size_t)fx.x * D + c0, acc);
+        const size_t off = dst_offset<T>(lay, grp_bytes, c0, fx.x);
+        if (boundary != nullptr) {
+            const Vec<T> bv = *reinterpret_cast<const Vec<T> *>(reinterpret_cast<const char *>(boundary) + off);
+#pragma unroll
+            for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<RED>(acc.v[k], bv.v[k]);
+        }
+        st_stream(reinterpret_cast<T *>(reinterpret_cast<char *>(dst) + off), acc);
     }
 }
 
 // fix-up, part 2: empty segments get the Nary identity (operator.cuh:53,66,79).  One warp per (segment, 128 columns).
 template <typename T, int RED>
 __global__ void __launch_bounds__(256) fill_identity_kernel(const int4 *__restrict__ fix, int num_fix,
-                                                            T *__restrict__ dst, int D) {
+                                                            T *__restrict__ dst, const T *__restrict__ boundary,
+                                                            int D, Layout lay, long long grp_bytes) {
     constexpr int V = VecN<T>::value;
     const int ncc = (D + 32 * V - 1) / (32 * V);
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -383,7 +429,11 @@ __global__ void __launch_bounds__(256) fill_identity_kernel(const int4 *__restri
     Vec<T> acc;
 #pragma unroll
     for (int k = 0; k < V; k++) acc.v[k] = nary_zero<RED, T>();
-    st_stream(dst + (size_t)__ldg(fix + f).x * D + c0, acc);
+    const size_t off = dst_offset<T>(lay, grp_bytes, c0, __ldg(fix + f).x);
+    if (boundary != nullptr) {  // Nary(identity, boundary) == boundary
+        acc = *reinterpret_cast<const Vec<T> *>(reinterpret_cast<const char *>(boundary) + off);
+    }
+    st_stream(reinterpret_cast<T *>(reinterpret_cast<char *>(dst) + off), acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -27,13 +27,13 @@ inline int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
 // whole items <= 2E/L+1; chunks <= E/L + #long with #long <= E/L
 inline int64_t max_items(int64_t E) { return 4 * ((E + kItemEdges - 1) / kItemEdges) + 8; }
 
-struct Layout {
+struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
 };
 
-Layout make_layout(int64_t N, int64_t E, int64_t R) {
-    Layout L;
+WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
+    WsLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(std::max<size_t>(bytes, 16)); return o; };
     const int64_t S[3] = {N, N, R};
@@ -185,7 +185,7 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         set_error("plan_build: num_node / num_edge / num_relation out of int32 range");
         return 1;
     }
-    const Layout L = make_layout(N, E, R);
+    const WsLayout L = make_layout(N, E, R);
     if (workspace_bytes < L.total || (workspace == nullptr && L.total > 0)) {
         set_error("plan_build: workspace too small");
         return 1;

@@ -1,0 +1,112 @@
+"""Head-major rspmm and the fused layer epilogue - the callers' side of the hot path.
+
+    rspmm_heads(edge_index, edge_type, edge_weight, relation (B,R,d), input (B,N,d), boundary (B,N,d)|None, sum, mul)
+        == generalized_rspmm on the transposed-and-flattened operands of /root/reference/ultra/layers.py:190-192,
+           folded with the boundary term (layers.py:199-207) and transposed back (layers.py:230) - without any of
+           those copies: the kernels address the (B, rows, d) layout directly.
+    nbfnet_update(x, u, linear, layer_norm, relu, shortcut)
+        == relu(layer_norm(linear(cat[x, u]))) (+ x)    layers.py:233-240 + models.py:158-160, one kernel, inference.
+"""
+import torch
+from torch import autograd
+
+from . import _capi
+from .plan import plan_cache, _DTYPE_ID, _stream_ptr
+
+
+def heads_layout_ok(input):
+    """The head-major kernels need head_dim * itemsize to be a multiple of the 128-byte column tile."""
+    return (input.is_cuda and input.dtype in _DTYPE_ID and input.dim() == 3
+            and (input.shape[-1] * input.element_size()) % 128 == 0)
+
+
+class _RSPMMHeadsFunction(autograd.Function):
+
+    @staticmethod
+    def forward(ctx, edge_index, edge_type, edge_weight, relation, input, boundary, sum, mul):
+        lib = _capi.lib()
+        sum_id, mul_id = _capi.SUM_IDS[sum], _capi.MUL_IDS[mul]
+        B, N, d = input.shape
+        R = relation.shape[1]
+        if relation.shape[0] != B or relation.shape[2] != d:
+            raise RuntimeError("rspmm_heads: relation must be (B, R, d) matching input (B, N, d)")
+        if boundary is not None and boundary.shape != input.shape:
+            raise RuntimeError("rspmm_heads: boundary must have the shape of input")
+        plan = plan_cache.get(edge_index, edge_type, N, R)
+        plan.bind_weight(edge_weight)
+        rel_c, in_c = relation.detach().contiguous(), input.detach().contiguous()
+        bnd_c = None if boundary is None else boundary.detach().contiguous()
+        output = torch.empty_like(in_c)
+        scratch = plan.scratch(B * d, input.dtype)
+        with torch.cuda.device(input.device):
+            rc = lib.ultra_rspmm_forward_heads(plan.handle, sum_id, mul_id, _DTYPE_ID[input.dtype], rel_c.data_ptr(),
+                                               in_c.data_ptr(), None if bnd_c is None else bnd_c.data_ptr(),
+                                               output.data_ptr(), B, d, scratch.data_ptr(), scratch.numel(),
+                                               _stream_ptr(input.device))
+        _capi.check(rc, "ultra_rspmm_forward_heads")
+        ctx.plan, ctx.ids, ctx.sum = plan, (sum_id, mul_id), sum
+        ctx.has_boundary = boundary is not None
+        ctx.save_for_backward(edge_weight, rel_c, in_c, output, bnd_c if bnd_c is not None else torch.empty(0))
+        return output
+
+    @staticmethod
+    def backward(ctx, output_grad):
+        if ctx.needs_input_grad[2]:
+            raise RuntimeError("rspmm_heads: edge_weight gradients need the flat path (generalized_rspmm)")
+        lib = _capi.lib()
+        edge_weight, rel_c, in_c, output, bnd_c = ctx.saved_tensors
+        plan = ctx.plan
+        plan.bind_weight(edge_weight)
+        B, N, d = in_c.shape
+        og = output_grad.contiguous()
+        relation_grad, input_grad = torch.empty_like(rel_c), torch.empty_like(in_c)
+        scratch = plan.scratch(B * d, in_c.dtype)
+        with torch.cuda.device(in_c.device):
+            rc = lib.ultra_rspmm_backward_heads(plan.handle, ctx.ids[0], ctx.ids[1], _DTYPE_ID[in_c.dtype],
+                                                rel_c.data_ptr(), in_c.data_ptr(), output.data_ptr(), og.data_ptr(),
+                                                relation_grad.data_ptr(), input_grad.data_ptr(), B, d,
+                                                scratch.data_ptr(), scratch.numel(), _stream_ptr(in_c.device))
+        _capi.check(rc, "ultra_rspmm_backward_heads")
+        boundary_grad = None
+        if ctx.has_boundary and ctx.needs_input_grad[5]:
+            # out = Nary(agg, boundary): d out / d boundary = 1 (sum) or [out == boundary] (min / max, operator.cuh:62,75)
+            boundary_grad = og if ctx.sum == "add" else og * (output == bnd_c).to(og.dtype)
+        return None, None, None, relation_grad, input_grad, boundary_grad, None, None
+
+
+def rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary=None, sum="add", mul="mul"):
+    if sum not in _capi.SUM_IDS or mul not in _capi.MUL_IDS:
+        raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`"
+                         % (sum, mul))
+    if not heads_layout_ok(input):
+        raise RuntimeError("rspmm_heads needs CUDA fp32/fp64 (B, N, d) input with d * itemsize % 128 == 0")
+    return _RSPMMHeadsFunction.apply(edge_index, edge_type, edge_weight, relation, input, boundary, sum, mul)
+
+
+def nbfnet_update_ok(x, u, linear, activation):
+    import torch.nn.functional as F
+    return (x.is_cuda and x.dtype == torch.float32 and u.dtype == torch.float32 and x.shape == u.shape
+            and x.shape[-1] == 64 and linear.in_features == 128 and linear.out_features == 64
+            and linear.weight.dtype == torch.float32 and (activation is None or activation is F.relu)
+            and not torch.is_grad_enabled())
+
+
+def nbfnet_update(x, u, linear, layer_norm=None, relu=True, shortcut=False):
+    """One-pass layer epilogue (inference).  x, u: (..., 64) fp32 CUDA; returns a tensor of x's shape."""
+    lib = _capi.lib()
+    xc, uc = x.contiguous(), u.contiguous()
+    out = torch.empty_like(xc)
+    wt = linear.weight.detach().t().contiguous()  # (128, 64); 32 KB
+    bias = linear.bias
+    gamma = layer_norm.weight if layer_norm is not None else None
+    beta = layer_norm.bias if layer_norm is not None else None
+    ptr = lambda t: None if t is None else t.detach().data_ptr()
+    rows = xc.numel() // 64
+    with torch.cuda.device(x.device):
+        rc = lib.ultra_nbfnet_update_f32(xc.data_ptr(), uc.data_ptr(), wt.data_ptr(), ptr(bias), ptr(gamma), ptr(beta),
+                                         out.data_ptr(), rows, 128, 64,
+                                         float(layer_norm.eps) if layer_norm is not None else 0.0,
+                                         1 if layer_norm is not None else 0, 1 if relu else 0, 1 if shortcut else 0,
+                                         _stream_ptr(x.device))
+    _capi.check(rc, "ultra_nbfnet_update_f32")
+    return out

@@ -12,6 +12,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .rspmm import generalized_rspmm
+from . import fused
 
 
 class GeneralizedRelationalConv(nn.Module):
@@ -38,8 +39,12 @@ class GeneralizedRelationalConv(nn.Module):
             self.relation_projection = nn.Sequential(nn.Linear(input_dim, input_dim), nn.ReLU(),
                                                      nn.Linear(input_dim, input_dim))
 
-    def forward(self, input, query, boundary, edge_index, edge_type, size, edge_weight=None):
-        """input, boundary: (B, N, d); query: (B, d_q); returns (B, N, output_dim).  layers.py:67-88."""
+    fuse = True  # class-wide switch for the head-major / fused-epilogue fast path (set False to force the restatement)
+
+    def forward(self, input, query, boundary, edge_index, edge_type, size, edge_weight=None, shortcut=False):
+        """input, boundary: (B, N, d); query: (B, d_q); returns (B, N, output_dim).  layers.py:67-88.
+        `shortcut=True` (not in the reference signature) also adds `input` to the result, i.e. the residual of the
+        Bellman-Ford loop (models.py:158-160), so that it can be folded into the fused epilogue."""
         batch_size = len(query)
         if self.dependent:
             relation = self.relation_linear(query).view(batch_size, self.num_relation, self.input_dim)
@@ -51,8 +56,30 @@ class GeneralizedRelationalConv(nn.Module):
             edge_weight = torch.ones(len(edge_type), device=input.device, dtype=input.dtype)
         if self.message_func not in self.message2mul:
             raise ValueError("Unknown message function `%s`" % self.message_func)
-        update = self.message_and_aggregate(edge_index, input, relation, boundary, edge_type, edge_weight, size[0])
-        return self.update(update, input)
+        fast = (self.fuse and self.aggregate_func in ("sum", "mean", "max") and fused.heads_layout_ok(input)
+                and not edge_weight.requires_grad and relation.dtype == input.dtype)
+        if fast:
+            update = self.message_and_aggregate_heads(edge_index, input, relation, boundary, edge_type, edge_weight,
+                                                      size[0])
+            if fused.nbfnet_update_ok(input, update, self.linear, self.activation):
+                return fused.nbfnet_update(input, update, self.linear, self.layer_norm,
+                                           relu=self.activation is not None, shortcut=shortcut)
+        else:
+            update = self.message_and_aggregate(edge_index, input, relation, boundary, edge_type, edge_weight, size[0])
+        output = self.update(update, input)
+        return output + input if shortcut else output
+
+    def message_and_aggregate_heads(self, edge_index, input, relation, boundary, edge_type, edge_weight, dim_size):
+        """Same result as message_and_aggregate for sum / mean / max, but the (B, N, d) state is consumed and produced
+        in place by the head-major kernels: no transpose copies, boundary folded into the store."""
+        mul = self.message2mul[self.message_func]
+        relation = relation.contiguous()  # materialises the (B, R, d) expand of the embedding mode (tiny)
+        if self.aggregate_func == "max":
+            return fused.rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary, sum="max", mul=mul)
+        update = fused.rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary, sum="add", mul=mul)
+        if self.aggregate_func == "mean":
+            update = update / self._degree_out(edge_index, dim_size, input).unsqueeze(0)
+        return update
 
     def message_and_aggregate(self, edge_index, input, relation, boundary, edge_type, edge_weight, dim_size):
         """layers.py:183-231: (B,N,d) -> (N,B*d) copies, rspmm, boundary as the self-loop message."""
@@ -114,9 +141,8 @@ def bellmanford_entity(layers, query, h_index, edge_index, edge_type, num_node, 
     size = (num_node, num_node)
     layer_input = boundary
     for li, layer in enumerate(layers):
-        hidden = layer(layer_input, query, boundary, edge_index, edge_type, size, edge_weight)
-        if short_cut and hidden.shape == layer_input.shape:
-            hidden = hidden + layer_input
+        residual = short_cut and layer.output_dim == layer_input.shape[-1]
+        hidden = layer(layer_input, query, boundary, edge_index, edge_type, size, edge_weight, shortcut=residual)
         if hook is not None:
             hook(li, hidden)
         layer_input = hidden

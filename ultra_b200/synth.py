@@ -72,3 +72,54 @@ def algorithmic_bytes(num_node, num_edge, num_relation, dim, elem=4):
 def compulsory_bytes(num_node, num_edge, num_relation, dim, elem=4):
     """Compulsory-traffic floor: input read once, output written once."""
     return elem * dim * (2 * num_node + num_relation) + 12 * num_edge + 4 * (num_node + 1)
+
+
+def relation_graph_of(edge_index, edge_type, num_node, num_relation):
+    """Torch-only restatement of build_relation_graph (/root/reference/ultra/tasks.py:144-199): relations become
+    nodes; 4 edge types (0 h2h, 1 t2t, 2 h2t, 3 t2h) connect relations that share a head/tail entity.  Only the
+    sparsity pattern of the four products is used by the reference, so dense boolean products suffice (R <= ~1.5k).
+    Returns (edge_index (2,E'), edge_type (E'), num_relation=4, num_node=R)."""
+    dev = edge_index.device
+    Eh = torch.zeros(num_node, num_relation, device=dev)
+    Et = torch.zeros(num_node, num_relation, device=dev)
+    Eh[edge_index[0], edge_type] = 1.0
+    Et[edge_index[1], edge_type] = 1.0
+    prods = [Eh.t() @ Eh, Et.t() @ Et, Eh.t() @ Et, Et.t() @ Eh]  # hh, tt, ht, th  (tasks.py:181-184)
+    eis, ets = [], []
+    for k, a in enumerate(prods):
+        idx = (a > 0).nonzero().t()
+        eis.append(idx)
+        ets.append(torch.full((idx.shape[1],), k, dtype=torch.long, device=dev))
+    return torch.cat(eis, dim=1), torch.cat(ets), 4, num_relation
+
+
+def synth_kg_torch(num_node, num_rel_base, num_triples, alpha=1.0, seed=0, device="cuda"):
+    """GPU generator for the large sweep graphs (same recipe as synth_kg, torch ops, not bit-identical to it)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def sampler(n):
+        if alpha == 0.0:
+            return lambda m: torch.randint(0, n, (m,), generator=g, device=device)
+        p = 1.0 / torch.arange(1, n + 1, dtype=torch.float64, device=device).pow(alpha)
+        cdf = torch.cumsum(p, 0)
+        cdf = cdf / cdf[-1]
+        perm = torch.randperm(n, generator=g, device=device)
+        return lambda m: perm[torch.searchsorted(cdf, torch.rand(m, generator=g, device=device, dtype=torch.float64)
+                                                 ).clamp_(max=n - 1)]
+    node, rel = sampler(num_node), sampler(num_rel_base)
+    keys = torch.empty(0, dtype=torch.long, device=device)
+    target = min(num_triples, num_node * num_node * num_rel_base)
+    while keys.numel() < target:
+        m = int((target - keys.numel()) * 1.5) + 1024
+        k = (node(m) * num_rel_base + rel(m)) * num_node + node(m)
+        keys = torch.unique(torch.cat([keys, k]))
+        if keys.numel() > target:
+            keys = keys[torch.randperm(keys.numel(), generator=g, device=device)[:target]]
+    keys = keys[torch.randperm(keys.numel(), generator=g, device=device)]
+    t = keys % num_node
+    hr = keys // num_node
+    r = hr % num_rel_base
+    h = hr // num_rel_base
+    edge_index = torch.stack([torch.cat([h, t]), torch.cat([t, h])])
+    edge_type = torch.cat([r, r + num_rel_base])
+    return edge_index, edge_type, 2 * num_rel_base
