@@ -343,11 +343,12 @@ def bench_layer(wl, device, world, rank):
         return float(t.item())
 
     with torch.no_grad():
-        layer_ms = timeit(lambda: layers[0](x, query, bd, ei, et, (N, N), w) + x)
+        layer_ms = timeit(lambda: layers[0](x, query, bd, ei, et, (N, N), w, shortcut=True))
         stack_ms = timeit(lambda: bellmanford_entity(layers, query, h_index, ei, et, N), reps=3, warm=1)
         info = {"layer_ms": layer_ms, "stack6_ms": stack_ms, "heads_per_gpu": B,
-                "what": "GeneralizedRelationalConv forward (distmult+sum, layer_norm, shortcut), fp32; non-rspmm parts "
-                        "are PyTorch ops (fused epilogue is SURVEY 8f row f2)"}
+                "what": "GeneralizedRelationalConv forward (distmult+sum, layer_norm, relu, shortcut), fp32: "
+                        "relation_projection MLP (PyTorch) + head-major rspmm with folded boundary + fused "
+                        "Linear/LayerNorm/ReLU/residual kernel (SURVEY 8f row f2); stack6 = 6-layer Bellman-Ford loop"}
         if world > 1:
             def stack_gather():
                 g = OverlappedStateGather(B * world)
