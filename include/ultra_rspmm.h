@@ -41,6 +41,14 @@ typedef struct ultra_rspmm_plan ultra_rspmm_plan; /* opaque host object */
 /* Library / build identification ("ultra_rspmm sm_100a <version>"). */
 const char *ultra_rspmm_version(void);
 
+/*
+ * Process-wide launch tunables.  "sm_limit": size the persistent grids for this many SMs (0 = all) so that a
+ * concurrent NCCL collective (the overlapped all-gather of node states, ultra_b200/shard.py) finds free SMs.
+ * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
+ */
+int ultra_rspmm_set_tunable(const char *name, int value);
+int ultra_rspmm_get_sm_limit(void);
+
 /* Message of the last failing call on this thread ("" if none). */
 const char *ultra_rspmm_last_error(void);
 

@@ -180,3 +180,37 @@ def test_c_abi_rejects_bad_arguments(cuda_device):
     assert rc != 0 and b"sum_op" in lib.ultra_rspmm_last_error()
     rc = lib.ultra_rspmm_forward(None, 0, 0, 0, xd.data_ptr(), xd.data_ptr(), xd.data_ptr(), 32, None, 0, None)
     assert rc != 0 and b"null plan" in lib.ultra_rspmm_last_error()
+
+
+def test_forward_backward_are_cuda_graph_capturable(cuda_device):
+    """The reference syncs the host on every call (sortedness assert, rspmm.py:15-17); with a cached plan the whole
+    forward+backward is stream-ordered, so it can be captured once and replayed (relation-graph regime)."""
+    from ultra_b200.rspmm import generalized_rspmm
+    d = cuda_device
+    ei, et, w, rel, x, og = random_case(51, 120, 3000, 4, 64, hub=500, unit_weight=True)
+    ei, et, w = ei.to(d), et.to(d), w.to(d)
+    s_rel, s_x, s_og = rel.to(d).requires_grad_(), x.to(d).requires_grad_(), og.to(d)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up outside capture: plan build, weight bind, scratch allocation
+        for _ in range(2):
+            out = generalized_rspmm(ei, et, w, s_rel, s_x, sum="add", mul="mul")
+            out.backward(s_og)
+            s_rel.grad = s_x.grad = None
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out = generalized_rspmm(ei, et, w, s_rel, s_x, sum="add", mul="mul")
+        g_out.backward(s_og)
+    g_xgrad, g_rgrad = s_x.grad, s_rel.grad
+    for seed in (1, 2):
+        gen = torch.Generator().manual_seed(seed)
+        nx, nrel = torch.randn(x.shape, generator=gen), torch.randn(rel.shape, generator=gen)
+        with torch.no_grad():
+            s_x.copy_(nx)
+            s_rel.copy_(nrel)
+        graph.replay()
+        e_out, _, e_rg, e_ig = oracle_all("add", "mul", ei.cpu(), et.cpu(), w.cpu(), nrel, nx, og)
+        assert_close_ref(g_out.detach(), e_out, "replayed forward")
+        assert_close_ref(g_xgrad, e_ig, "replayed input_grad")
+        assert_close_ref(g_rgrad, e_rg, "replayed relation_grad")

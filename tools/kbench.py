@@ -36,9 +36,15 @@ def main():
     ap.add_argument("--ops", default="add_mul")
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--peak", type=float, default=6583.2)
+    ap.add_argument("--l2-percent", type=int, default=0)
+    ap.add_argument("--sm-limit", type=int, default=0)
     args = ap.parse_args()
     d = torch.device("cuda:0")
     lib = _capi.lib()
+    if args.l2_percent:
+        _capi.set_tunable("l2_percent", args.l2_percent)
+    if args.sm_limit:
+        _capi.set_tunable("sm_limit", args.sm_limit)
     for alpha in [float(a) for a in args.alphas.split(",")]:
         ei, et, R, N = synth_scale(args.scale, alpha=alpha, seed=1234)
         E = ei.shape[1]

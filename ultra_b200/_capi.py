@@ -17,6 +17,8 @@ _vp, _i64, _int, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_s
 SYMBOLS = {
     "ultra_rspmm_version": (ctypes.c_char_p, []),
     "ultra_rspmm_last_error": (ctypes.c_char_p, []),
+    "ultra_rspmm_set_tunable": (_int, [ctypes.c_char_p, _int]),
+    "ultra_rspmm_get_sm_limit": (_int, []),
     "ultra_rspmm_plan_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ultra_rspmm_plan_build": (_int, [ctypes.POINTER(_vp), _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_plan_destroy": (None, [_vp]),
@@ -57,6 +59,10 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def set_tunable(name, value):
+    check(lib().ultra_rspmm_set_tunable(name.encode(), int(value)), "ultra_rspmm_set_tunable")
 
 
 def check(rc, what):

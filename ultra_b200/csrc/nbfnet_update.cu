@@ -160,6 +160,8 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
     int sms = 148;
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (err != cudaSuccess) { set_error(std::string("nbfnet_update: ") + cudaGetErrorString(err)); return 2; }
+    const int sm_limit = ultra_rspmm_get_sm_limit();
+    if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
     const long long tiles = (num_rows + kBM - 1) / kBM;
     const int grid = (int)(tiles < 2LL * sms ? tiles : 2LL * sms);
     nbfnet_update_kernel<<<grid, kThreads, kSmemBytes, stream>>>(x, u, weight_t, bias, ln_gamma, ln_beta, out,

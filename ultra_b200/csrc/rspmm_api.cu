@@ -2,6 +2,7 @@
 // launch geometry.  Replaces the host launchers of the reference (rspmm.cu:216-267 forward, :269-351 backward).
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -25,7 +26,11 @@ namespace {
         }                                                                                      \
     } while (0)
 
-constexpr size_t kSlabSmemLimit = 100 * 1024;  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
+constexpr size_t kSlabSmemLimit = 100 * 1024;
+
+// process-wide launch tunables (ultra_rspmm_set_tunable)
+std::atomic<int> g_sm_limit{0};          // 0 = use every SM; >0 = size persistent grids for this many SMs
+std::atomic<int> g_l2_percent{25};       // share of L2 the concurrently gathered tiles may occupy  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
 
 template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
     if (D % VecN<T>::value != 0) return false;
@@ -89,7 +94,8 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
     if (p.num_warp_items > 0) {
-        const int ctas = plan->sm_count * 2;
+        const int sm_limit = g_sm_limit.load();
+        const int ctas = ((sm_limit > 0 && sm_limit < plan->sm_count) ? sm_limit : plan->sm_count) * 2;
         // items per warp per unit: 2 when that still leaves every CTA several units
         int ipw = 2;
         auto units_per_tile = [&](int k) { return (p.num_warp_items + kCtaWarps * k - 1) / (kCtaWarps * k); };
@@ -99,7 +105,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         p.total_units = (long long)p.units_per_tile * p.num_tiles;
         // tile-major walk: each CTA takes `run` consecutive units, so ~ctas*run/units_per_tile tiles are in
         // flight; keep their gathered footprint (segments' source rows x 128 B) within a fraction of L2.
-        const size_t l2_budget = plan->l2_bytes ? plan->l2_bytes / 4 : (size_t)24 << 20;
+        const size_t l2_budget = (plan->l2_bytes ? plan->l2_bytes : (size_t)96 << 20) / 100 * (size_t)g_l2_percent.load();
         const size_t rows_gathered = (size_t)std::max<int64_t>(plan->N, 1);
         const double tiles_in_flight = std::max(1.0, (double)l2_budget / ((double)rows_gathered * kTileBytes));
         long long run = (long long)(tiles_in_flight * p.units_per_tile / ctas);
@@ -206,6 +212,17 @@ using namespace ultra;
 extern "C" {
 
 const char *ultra_rspmm_version(void) { return "ultra_rspmm sm_100a 0.1.0"; }
+
+int ultra_rspmm_set_tunable(const char *name, int value) {
+    if (name == nullptr) { set_error("set_tunable: null name"); return 1; }
+    const std::string n(name);
+    if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
+    if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
+    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent)");
+    return 1;
+}
+
+int ultra_rspmm_get_sm_limit(void) { return g_sm_limit.load(); }
 
 const char *ultra_rspmm_last_error(void) { return g_last_error.c_str(); }
 

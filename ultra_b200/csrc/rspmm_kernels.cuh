@@ -19,7 +19,9 @@
 // at once with no cross-lane traffic.  CTAs are persistent and walk (tile, item-chunk) units TILE-MAJOR so
 // that the concurrently active tiles of `input` (N x 128 B each) stay L2-resident: HBM sees ~compulsory
 // traffic and the gathers are served by L2.  The relation tile (R x 128 B) is staged in shared memory once per
-// (CTA, tile) visit.
+// (CTA, tile) visit by TMA bulk copies (cp.async.bulk, one 128-byte row slice each, mbarrier completion).  The
+// per-edge gathers themselves stay LDG.128 -> registers: tools/gather_microbench.cu measures 128-byte TMA bulk
+// gathers at <= the LDG rate (both ~7 TB/s, the L2 limit) while costing an smem round trip and the L1 hits.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -321,6 +323,14 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
     T *rel_s = reinterpret_cast<T *>(smem_raw);
     const int warp = threadIdx.x >> 5;
     const uint32_t rel_s_addr = (uint32_t)__cvta_generic_to_shared(rel_s);
+    __shared__ __align__(8) unsigned long long slab_bar;  // mbarrier for the TMA-staged relation tile
+    const uint32_t slab_bar_addr = (uint32_t)__cvta_generic_to_shared(&slab_bar);
+    unsigned slab_phase = 0;
+    if (N::rel && REL_SMEM) {
+        if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(slab_bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     const bool use_w = p.w != nullptr && __ldg(p.w_nonunit) != 0;  // uniform over the grid
     int cur_tile = -1;
 
@@ -331,22 +341,42 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
             const int tile = (int)(unit / p.units_per_tile);
             const int chunk = (int)(unit - (long long)tile * p.units_per_tile);
             if (N::rel && REL_SMEM && tile != cur_tile) {
-                __syncthreads();  // everyone is done with the previous tile's slab
-                const int nvec = p.R * kLanesPerEdge;
-                for (int idx = threadIdx.x; idx < nvec; idx += kCtaThreads) {
-                    const int r = idx >> 3, qq = idx & 7;
-                    const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
-                    const int cin = tin * TILE + qq * V;
-                    Vec<T> x;
+                __syncthreads();  // everyone is done reading the previous tile's relation rows
+                const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
+                const char *src = reinterpret_cast<const char *>(p.relation) + (size_t)grp * p.lay.grp_rel_bytes +
+                                  (size_t)tin * kTileBytes;
+                if ((tin + 1) * TILE <= p.lay.group_cols) {
+                    // full tile: one TMA bulk copy (UBLKCP) of 128 bytes per relation row, completion on an mbarrier
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads -> async writes
+                    if (threadIdx.x == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                     ::"r"(slab_bar_addr), "r"(p.R * kTileBytes) : "memory");
+                    for (int r = threadIdx.x; r < p.R; r += kCtaThreads)
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                            ::"r"(rel_s_addr + (uint32_t)r * kTileBytes),
+                              "l"(src + (unsigned long long)(unsigned)r * p.lay.row_bytes), "r"(kTileBytes),
+                              "r"(slab_bar_addr) : "memory");
+                    unsigned done = 0;
+                    while (!done)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+                                     "selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(slab_bar_addr), "r"(slab_phase)
+                                     : "memory");
+                    slab_phase ^= 1u;
+                } else {  // ragged last tile of a group: vector loads with zero fill
+                    const int nvec = p.R * kLanesPerEdge;
+                    for (int idx = threadIdx.x; idx < nvec; idx += kCtaThreads) {
+                        const int r = idx >> 3, qq = idx & 7;
+                        const int cin = tin * TILE + qq * V;
+                        Vec<T> x;
 #pragma unroll
-                    for (int k = 0; k < V; k++) x.v[k] = T(0);
-                    if (cin < p.lay.group_cols)
-                        x = ld_gather(reinterpret_cast<const T *>(
-                            reinterpret_cast<const char *>(p.relation) + (size_t)grp * p.lay.grp_rel_bytes +
-                            (size_t)r * p.lay.row_bytes + (size_t)cin * sizeof(T)));
-                    *reinterpret_cast<Vec<T> *>(rel_s + r * TILE + qq * V) = x;
+                        for (int k = 0; k < V; k++) x.v[k] = T(0);
+                        if (cin < p.lay.group_cols)
+                            x = ld_gather(reinterpret_cast<const T *>(src + (size_t)r * p.lay.row_bytes + qq * 16));
+                        *reinterpret_cast<Vec<T> *>(rel_s + r * TILE + qq * V) = x;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 cur_tile = tile;
             }
 #pragma unroll 1

@@ -15,6 +15,7 @@ that are visible to a caller, all deliberate:
     path returns zeros that autograd then discards, rspmm.cu:295,312-331).
 """
 import ctypes
+import os
 import sys
 import threading
 
@@ -128,7 +129,7 @@ def _run_backward(plan, sum_id, mul_id, relation, input, output, output_grad, ne
 
 
 # host staging: device slab buffers are cached per (plan, dim, dtype)
-_HOST_SLAB_DIM = 512
+_HOST_SLAB_DIM = int(os.environ.get("ULTRA_RSPMM_HOST_SLAB", "512"))
 
 
 def _run_forward_host(plan, sum_id, mul_id, relation, input, device, slab_dim=None):
