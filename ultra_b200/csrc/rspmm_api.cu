@@ -106,7 +106,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         // tile-major walk: each CTA takes `run` consecutive units, so ~ctas*run/units_per_tile tiles are in
         // flight; keep their gathered footprint (segments' source rows x 128 B) within a fraction of L2.
         const size_t l2_budget = (plan->l2_bytes ? plan->l2_bytes : (size_t)96 << 20) / 100 * (size_t)g_l2_percent.load();
-        const size_t rows_gathered = (size_t)std::max<int64_t>(plan->N, 1);
+        const size_t rows_gathered = (size_t)std::max<int64_t>(plan->N, 1) * Nd::gathers;  // matrices gathered from
         const double tiles_in_flight = std::max(1.0, (double)l2_budget / ((double)rows_gathered * kTileBytes));
         long long run = (long long)(tiles_in_flight * p.units_per_tile / ctas);
         run = std::max<long long>(1, std::min<long long>(run, p.units_per_tile));

@@ -140,7 +140,8 @@ template <int MODE, int SUM, int MUL> struct Needs {
     static constexpr bool rel = (MODE == FWD) || (MODE == BWD_IN && (MUL == M_MUL || SUM != S_ADD));
     static constexpr bool self = (MODE != FWD) && (SUM != S_ADD);   // the segment's own input / relation row
     static constexpr int red = (MODE == FWD) ? SUM : S_ADD;
-    static constexpr int unroll = (MODE == FWD) ? 4 : ((out || inb) ? 2 : 4);
+    static constexpr int gathers = 1 + (out ? 1 : 0) + (inb ? 1 : 0);  // row slices fetched per edge
+    static constexpr int unroll = (gathers == 1 || (gathers == 2 && SUM == S_ADD)) ? 4 : 2;  // register budget: 64
 };
 
 // shared-memory vector load through a 32-bit shared-window address (address math stays in 32 bits)
