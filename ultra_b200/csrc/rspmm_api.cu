@@ -90,7 +90,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     p.num_warp_items = so.num_items / kSubPerWarp;
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
     p.dst = dst; p.partial = scratch; p.boundary = boundary; p.lay = lay;
-    p.D = (int)D; p.R = (int)plan->R;
+    p.D = (int)D; p.R = (int)plan->R; p.N = (int)plan->N;
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
     if (p.num_warp_items > 0) {
@@ -110,23 +110,32 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         const double tiles_in_flight = std::max(1.0, (double)l2_budget / ((double)rows_gathered * kTileBytes));
         long long run = (long long)(tiles_in_flight * p.units_per_tile / ctas);
         run = std::max<long long>(1, std::min<long long>(run, p.units_per_tile));
+        // ... but never so long that CTAs go idle: keep >= 4 blocks of `run` units per CTA when the work allows it
+        // (small graphs have huge tiles_in_flight; without this cap each CTA would own a whole tile and a
+        // 32-tile problem would occupy 32 of 296 CTAs)
+        run = std::max<long long>(1, std::min<long long>(run, p.total_units / (4LL * ctas)));
         p.run = (int)run;
         const long long nblk = (p.total_units + p.run - 1) / p.run;
         const int grid = (int)std::min<long long>(nblk, ctas);
 
-        const size_t slab = (size_t)plan->R * kTileBytes;
-        const bool rel_smem = Nd::rel && slab <= kSlabSmemLimit;
-        if (rel_smem) {
-            auto kern = seg_reduce_kernel<T, MODE, SUM, MUL, true>;
-            static thread_local int attr_set_for = -1;  // per (instantiation, thread); cheap to redo per device
-            if (attr_set_for != plan->device) {
+        // shared-memory residency: relation tile (R x 128 B) and, for small graphs, the gathered matrix' tile too
+        const size_t rel_bytes = Nd::rel ? (size_t)plan->R * kTileBytes : 0;
+        const size_t g1_bytes = (size_t)plan->N * kTileBytes;
+        int sm_mode = 0;
+        if (rel_bytes + g1_bytes <= kSlabSmemLimit) sm_mode = 2;
+        else if (Nd::rel && rel_bytes <= kSlabSmemLimit) sm_mode = 1;
+        auto launch = [&](auto kern, size_t smem) -> int {
+            if (smem > 48 * 1024) {  // opt-in above 48 KB; cudaFuncSetAttribute is cheap and idempotent
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemLimit));
-                attr_set_for = plan->device;
             }
-            kern<<<grid, kCtaThreads, slab, stream>>>(p);
-        } else {
-            seg_reduce_kernel<T, MODE, SUM, MUL, false><<<grid, kCtaThreads, 0, stream>>>(p);
-        }
+            kern<<<grid, kCtaThreads, smem, stream>>>(p);
+            return 0;
+        };
+        int lrc = 0;
+        if (sm_mode == 2) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 2>, rel_bytes + g1_bytes);
+        else if (sm_mode == 1) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 1>, rel_bytes);
+        else lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 0>, 0);
+        if (lrc) return lrc;
         CUDA_TRY(cudaGetLastError());
     }
     const int ncc = (int)((D + 32 * V - 1) / (32 * V));

@@ -126,6 +126,7 @@ template <typename T> struct SegParams {
     Layout lay;         // where tile t / row r of the feature matrices live (flat (rows, D) or head-major (B, rows, d))
     int D;
     int R;
+    int N;
     int num_tiles;
     int units_per_tile;
     int items_per_warp;
@@ -163,8 +164,11 @@ template <typename T> __device__ __forceinline__ Vec<T> ld_row(const char *base,
 // One warp walks 4 items (one per 8-lane sub-group) of one column tile.
 //   UNITW : every edge weight is 1 (device flag) -> no weight loads, y = Bin(rel, in) (1 * x == x exactly)
 // The loop has a predicate-free main part (all 4 sub-groups still have edges) and a predicated tail.
-template <typename T, int MODE, int SUM, int MUL, bool REL_SMEM, bool UNITW>
-__device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, int tile, uint32_t rel_s_addr) {
+template <typename T, int MODE, int SUM, int MUL, int SM, bool UNITW>
+__device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, int tile, uint32_t rel_s_addr,
+                                                uint32_t g1_s_addr) {
+    constexpr bool REL_SMEM = SM >= 1;
+    constexpr bool G1_SMEM = SM == 2;
     using N = Needs<MODE, SUM, MUL>;
     constexpr int V = VecN<T>::value;
     constexpr int TILE = kLanesPerEdge * V;
@@ -202,6 +206,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const char *bnd_c = reinterpret_cast<const char *>(p.boundary) + off_n;
     const bool has_bnd = (MODE == FWD) && p.boundary != nullptr;
     const uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;
+    const uint32_t g1_q = g1_s_addr + (uint32_t)q * 16u;
 
     Vec<T> acc, self;
 #pragma unroll
@@ -225,7 +230,8 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
         Vec<T> g1[U], g2[U], g3[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            g1[u] = ld_row<T>(g1_c, (unsigned)m[u].x, row_bytes);
+            if (G1_SMEM) g1[u] = lds_vec<T>(g1_q + ((uint32_t)m[u].x << 7));
+            else g1[u] = ld_row<T>(g1_c, (unsigned)m[u].x, row_bytes);
             if (N::out) g2[u] = ld_row<T>(out_c, (unsigned)m[u].x, row_bytes);
             if (N::inb) g3[u] = ld_row<T>(in_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
         }
@@ -309,25 +315,65 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     }
 }
 
-template <typename T, int MODE, int SUM, int MUL, bool REL_SMEM>
-__device__ __forceinline__ void walk_items(const SegParams<T> &p, int wi, int tile, uint32_t rel_s_addr, bool use_w) {
-    if (use_w) walk_items_impl<T, MODE, SUM, MUL, REL_SMEM, false>(p, wi, tile, rel_s_addr);
-    else walk_items_impl<T, MODE, SUM, MUL, REL_SMEM, true>(p, wi, tile, rel_s_addr);
+template <typename T, int MODE, int SUM, int MUL, int SM>
+__device__ __forceinline__ void walk_items(const SegParams<T> &p, int wi, int tile, uint32_t rel_s_addr,
+                                           uint32_t g1_s_addr, bool use_w) {
+    if (use_w) walk_items_impl<T, MODE, SUM, MUL, SM, false>(p, wi, tile, rel_s_addr, g1_s_addr);
+    else walk_items_impl<T, MODE, SUM, MUL, SM, true>(p, wi, tile, rel_s_addr, g1_s_addr);
 }
 
-template <typename T, int MODE, int SUM, int MUL, bool REL_SMEM>
+// Stage `nrows` 128-byte row slices (row r at src + r * row_bytes) into shared memory at smem_addr + r * 128.
+//   full tile   : one TMA bulk copy (cp.async.bulk -> UBLKCP) per row; completion is signalled on the CTA's mbarrier
+//                 (the caller has already posted expect_tx for the bytes and waits on it afterwards)
+//   ragged tile : 128-bit vector loads with zero fill (caller __syncthreads afterwards)
+template <typename T>
+__device__ __forceinline__ void stage_rows(uint32_t smem_addr, const char *src, int nrows, unsigned row_bytes,
+                                           bool full, int valid_cols, uint32_t bar_addr) {
+    constexpr int V = VecN<T>::value;
+    if (full) {
+        for (int r = threadIdx.x; r < nrows; r += kCtaThreads)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr + (uint32_t)r * kTileBytes),
+                           "l"(src + (unsigned long long)(unsigned)r * row_bytes), "r"(kTileBytes), "r"(bar_addr)
+                         : "memory");
+    } else {
+        for (int idx = threadIdx.x; idx < nrows * kLanesPerEdge; idx += kCtaThreads) {
+            const int r = idx >> 3, qq = idx & 7;
+            Vec<T> x;
+#pragma unroll
+            for (int k = 0; k < V; k++) x.v[k] = T(0);
+            if (qq * V < valid_cols) x = ld_gather(reinterpret_cast<const T *>(src + (size_t)r * row_bytes + qq * 16));
+            if constexpr (sizeof(T) == 4)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr + (uint32_t)idx * 16u),
+                             "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3]) : "memory");
+            else
+                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(smem_addr + (uint32_t)idx * 16u), "d"(x.v[0]),
+                             "d"(x.v[1]) : "memory");
+        }
+    }
+}
+
+// SM: what lives in shared memory for the current column tile
+//   0  nothing (relation rows come through L1/L2)
+//   1  the relation tile (R x 128 B)
+//   2  the relation tile (if the op needs it) AND the gathered matrix' tile (N x 128 B: input for FWD, output_grad
+//      for the backward passes) - small graphs such as ULTRA's relation graph (N = #relations <= ~800): every gather
+//      becomes an LDS.128 (half the L1 data-pipe cost of an LDG.128) and L2 sees only the staging traffic
+template <typename T, int MODE, int SUM, int MUL, int SM>
 __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegParams<T> p) {
     using N = Needs<MODE, SUM, MUL>;
     constexpr int V = VecN<T>::value;
     constexpr int TILE = kLanesPerEdge * V;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *rel_s = reinterpret_cast<T *>(smem_raw);
+    constexpr bool kRelS = N::rel && SM >= 1;
+    constexpr bool kG1S = SM == 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
-    const uint32_t rel_s_addr = (uint32_t)__cvta_generic_to_shared(rel_s);
-    __shared__ __align__(8) unsigned long long slab_bar;  // mbarrier for the TMA-staged relation tile
+    const uint32_t rel_s_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t g1_s_addr = rel_s_addr + (kRelS ? (uint32_t)p.R * kTileBytes : 0u);
+    __shared__ __align__(8) unsigned long long slab_bar;  // mbarrier of the TMA-staged tiles
     const uint32_t slab_bar_addr = (uint32_t)__cvta_generic_to_shared(&slab_bar);
     unsigned slab_phase = 0;
-    if (N::rel && REL_SMEM) {
+    if (kRelS || kG1S) {
         if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(slab_bar_addr));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
@@ -341,41 +387,31 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
             if (unit >= p.total_units) break;
             const int tile = (int)(unit / p.units_per_tile);
             const int chunk = (int)(unit - (long long)tile * p.units_per_tile);
-            if (N::rel && REL_SMEM && tile != cur_tile) {
-                __syncthreads();  // everyone is done reading the previous tile's relation rows
+            if ((kRelS || kG1S) && tile != cur_tile) {
+                __syncthreads();  // everyone is done reading the previous tile's rows
                 const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
-                const char *src = reinterpret_cast<const char *>(p.relation) + (size_t)grp * p.lay.grp_rel_bytes +
-                                  (size_t)tin * kTileBytes;
-                if ((tin + 1) * TILE <= p.lay.group_cols) {
-                    // full tile: one TMA bulk copy (UBLKCP) of 128 bytes per relation row, completion on an mbarrier
+                const bool full = (tin + 1) * TILE <= p.lay.group_cols;
+                const int valid_cols = p.lay.group_cols - tin * TILE;
+                const char *rel_src = reinterpret_cast<const char *>(p.relation) +
+                                      (size_t)grp * p.lay.grp_rel_bytes + (size_t)tin * kTileBytes;
+                const char *g1_src = reinterpret_cast<const char *>(MODE == FWD ? p.input : p.outgrad) +
+                                     (size_t)grp * p.lay.grp_node_bytes + (size_t)tin * kTileBytes;
+                if (full) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads -> async writes
                     if (threadIdx.x == 0)
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                                     ::"r"(slab_bar_addr), "r"(p.R * kTileBytes) : "memory");
-                    for (int r = threadIdx.x; r < p.R; r += kCtaThreads)
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                            ::"r"(rel_s_addr + (uint32_t)r * kTileBytes),
-                              "l"(src + (unsigned long long)(unsigned)r * p.lay.row_bytes), "r"(kTileBytes),
-                              "r"(slab_bar_addr) : "memory");
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(slab_bar_addr),
+                                     "r"(((kRelS ? p.R : 0) + (kG1S ? p.N : 0)) * kTileBytes) : "memory");
+                }
+                if (kRelS) stage_rows<T>(rel_s_addr, rel_src, p.R, p.lay.row_bytes, full, valid_cols, slab_bar_addr);
+                if (kG1S) stage_rows<T>(g1_s_addr, g1_src, p.N, p.lay.row_bytes, full, valid_cols, slab_bar_addr);
+                if (full) {
                     unsigned done = 0;
                     while (!done)
                         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
                                      "selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(slab_bar_addr), "r"(slab_phase)
                                      : "memory");
                     slab_phase ^= 1u;
-                } else {  // ragged last tile of a group: vector loads with zero fill
-                    const int nvec = p.R * kLanesPerEdge;
-                    for (int idx = threadIdx.x; idx < nvec; idx += kCtaThreads) {
-                        const int r = idx >> 3, qq = idx & 7;
-                        const int cin = tin * TILE + qq * V;
-                        Vec<T> x;
-#pragma unroll
-                        for (int k = 0; k < V; k++) x.v[k] = T(0);
-                        if (cin < p.lay.group_cols)
-                            x = ld_gather(reinterpret_cast<const T *>(src + (size_t)r * p.lay.row_bytes + qq * 16));
-                        *reinterpret_cast<Vec<T> *>(rel_s + r * TILE + qq * V) = x;
-                    }
+                } else {
                     __syncthreads();
                 }
                 cur_tile = tile;
@@ -383,7 +419,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegPar
 #pragma unroll 1
             for (int k = 0; k < p.items_per_warp; k++) {
                 const int wi = (chunk * p.items_per_warp + k) * kCtaWarps + warp;
-                if (wi < p.num_warp_items) walk_items<T, MODE, SUM, MUL, REL_SMEM>(p, wi, tile, rel_s_addr, use_w);
+                if (wi < p.num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, use_w);
             }
         }
     }
