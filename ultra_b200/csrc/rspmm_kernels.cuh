@@ -205,8 +205,12 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     char *dst_c = reinterpret_cast<char *>(p.dst) + (MODE == BWD_REL ? off_r : off_n);
     const char *bnd_c = reinterpret_cast<const char *>(p.boundary) + off_n;
     const bool has_bnd = (MODE == FWD) && p.boundary != nullptr;
-    const uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;
-    const uint32_t g1_q = g1_s_addr + (uint32_t)q * 16u;
+    uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;
+    uint32_t g1_q = g1_s_addr + (uint32_t)q * 16u;
+    // Pin the per-lane bases in registers: otherwise ptxas keeps "uniform base + lane offset" apart and re-adds the
+    // uniform half for every gather (IMAD.WIDE + IADD3 + IADD3.X instead of one IMAD.WIDE), and rematerialises the
+    // shared-window base (S2UR/ULEA) every iteration.
+    asm volatile("" : "+l"(g1_c), "+l"(out_c), "+l"(in_c), "+l"(rel_c), "+r"(rel_q), "+r"(g1_q));
 
     Vec<T> acc, self;
 #pragma unroll
@@ -244,8 +248,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                 else rr[u] = ld_row<T>(rel_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
+        auto consume = [&](int u) {
             Vec<T> nxt;
 #pragma unroll
             for (int k = 0; k < V; k++) {
@@ -280,21 +283,34 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             }
 #pragma unroll
             for (int k = 0; k < V; k++) acc.v[k] = ok[u] ? nxt.v[k] : acc.v[k];
-            // segment end inside a whole-segment item: emit the finished row, start the next one
-            if (m[u].y < 0 && ok[u] && slot == -1) {
-                if (st_ok) {
-                    if (has_bnd) {
-                        const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
+        };
+        // one row-end test for the whole group of U edges (row ends are rare: the common path is pure FMA)
+        int any = 0;
 #pragma unroll
-                        for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<N::red>(acc.v[k], bv.v[k]);
+        for (int u = 0; u < U; u++) any |= m[u].y;
+        if (!(any < 0 && slot == -1)) {
+#pragma unroll
+            for (int u = 0; u < U; u++) consume(u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                consume(u);
+                // segment end inside a whole-segment item: emit the finished row, start the next one
+                if (m[u].y < 0 && ok[u]) {
+                    if (st_ok) {
+                        if (has_bnd) {
+                            const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
+#pragma unroll
+                            for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<N::red>(acc.v[k], bv.v[k]);
+                        }
+                        st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
                     }
-                    st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
-                }
 #pragma unroll
-                for (int k = 0; k < V; k++) acc.v[k] = nary_zero<N::red, T>();
-                j++;
-                seg = (unsigned)__ldg(p.nonempty + j);  // padded by one entry (0), so this is always a valid row
-                if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
+                    for (int k = 0; k < V; k++) acc.v[k] = nary_zero<N::red, T>();
+                    j++;
+                    seg = (unsigned)__ldg(p.nonempty + j);  // padded by one entry (0): always a valid row
+                    if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
+                }
             }
         }
     };
