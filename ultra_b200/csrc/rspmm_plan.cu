@@ -198,11 +198,15 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
     auto *plan = new ultra_rspmm_plan();
     plan->N = N; plan->E = E; plan->R = R;
     CUDA_TRY(cudaGetDevice(&plan->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, plan->device));
-    plan->sm_count = prop.multiProcessorCount;
-    plan->l2_bytes = (size_t)prop.l2CacheSize;
-    plan->smem_optin = prop.sharedMemPerBlockOptin;
+    {   // cudaGetDeviceProperties costs tens of ms per call; three attribute queries are microseconds
+        int sms = 0, l2 = 0, smem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, plan->device));
+        CUDA_TRY(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device));
+        plan->sm_count = sms;
+        plan->l2_bytes = (size_t)l2;
+        plan->smem_optin = (size_t)smem;
+    }
 
     const int64_t S[3] = {N, N, R};
     for (int o = 0; o < 3; o++) {
