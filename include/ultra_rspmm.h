@@ -112,6 +112,17 @@ int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, i
                          size_t scratch_bytes, void *stream);
 
 /*
+ * PNA aggregation in ONE pass: the reference issues four rspmm calls over the same edges
+ * (/root/reference/ultra/layers.py:211-215: sum, sum over (relation**2, input**2), max, min); this entry point
+ * gathers every row slice once and produces all four.  output4 is (4, num_node, dim): [0] sum, [1] sum of squares,
+ * [2] max, [3] min, each exactly what the corresponding ultra_rspmm_forward call would write.  scratch must hold
+ * 4 * ultra_rspmm_scratch_bytes(plan, dim, dtype).  Forward only: gradients compose from the four backward calls.
+ */
+int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype, const void *relation,
+                            const void *input, void *output4, int64_t dim, void *scratch, size_t scratch_bytes,
+                            void *stream);
+
+/*
  * Head-major variants: the NBFNet layer keeps its state as (num_heads, rows, head_dim) = (B, N, d); the reference
  * transposes it into (N, B*d) copies before every rspmm call and back afterwards
  * (/root/reference/ultra/layers.py:190-192,230).  These entry points read and write the (B, rows, d) layout

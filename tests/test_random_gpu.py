@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import OPS, oracle_all
-from test_rspmm_gpu import run_ours, check_against
+from helpers import OPS, oracle_all, assert_close_with_truth, assert_equal_values
+from test_rspmm_gpu import run_ours
 
 pytestmark = pytest.mark.gpu
 
@@ -41,7 +41,18 @@ def test_random_problem(cuda_device, seed):
     rng = np.random.default_rng(1000 + seed)
     ei, et, w, rel, x, og = draw_case(rng)
     sum, mul = OPS[int(rng.integers(len(OPS)))]
+    what = "seed %d N=%d E=%d R=%d D=%d %s %s-%s " % (seed, x.shape[0], ei.shape[1], rel.shape[0], x.shape[1], x.dtype,
+                                                       sum, mul)
     ours = run_ours(sum, mul, ei, et, w, rel, x, og)
-    check_against(sum, mul, ours, oracle_all(sum, mul, ei, et, w, rel, x, og),
-                  "seed %d N=%d E=%d R=%d D=%d %s %s-%s " % (seed, x.shape[0], ei.shape[1], rel.shape[0], x.shape[1],
-                                                              x.dtype, sum, mul))
+    ref = oracle_all(sum, mul, ei, et, w, rel, x, og)
+    # fp64 evaluation of the same algorithm = ground truth for the error budget of very long rows
+    truth = oracle_all(sum, mul, ei, et, w.double(), rel.double(), x.double(), og.double())
+    names = ("forward", "weight_grad", "relation_grad", "input_grad")
+    for name, a, r, t in zip(names, ours, ref, truth):
+        if name == "forward" and sum != "add":
+            assert_equal_values(a, r, what + name)   # min / max: no re-association, bit-exact by value
+        elif sum != "add" and x.dtype == torch.float32:
+            # min/max gradients route through exact ties; the fp64 run can pick other ties -> compare to the fp32 oracle
+            assert_close_with_truth(a, r, r, what + name)
+        else:
+            assert_close_with_truth(a, r, t, what + name)

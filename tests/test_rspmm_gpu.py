@@ -214,3 +214,35 @@ def test_forward_backward_are_cuda_graph_capturable(cuda_device):
         assert_close_ref(g_out.detach(), e_out, "replayed forward")
         assert_close_ref(g_xgrad, e_ig, "replayed input_grad")
         assert_close_ref(g_rgrad, e_rg, "replayed relation_grad")
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 96), (torch.float64, 40)])
+def test_pna_one_pass_equals_four_calls(cuda_device, mul, dtype, D):
+    """generalized_rspmm_pna == the reference layer's four rspmm calls (layers.py:211-215), forward and backward."""
+    from ultra_b200.rspmm import generalized_rspmm, generalized_rspmm_pna
+    d = cuda_device
+    ei, et, w, rel, x, og = random_case(61, 150, 5000, 7, D, dtype=dtype, hub=900)
+    ei, et, w = ei.to(d), et.to(d), w.to(d)
+    g = torch.Generator().manual_seed(62)
+    ogs = [torch.randn(x.shape, generator=g, dtype=dtype).to(d) for _ in range(4)]
+    r1, x1 = rel.to(d).requires_grad_(), x.to(d).requires_grad_()
+    outs = generalized_rspmm_pna(ei, et, w, r1, x1, mul=mul)
+    sum((o * g_).sum() for o, g_ in zip(outs, ogs)).backward()
+    r2, x2 = rel.to(d).requires_grad_(), x.to(d).requires_grad_()
+    refs = [generalized_rspmm(ei, et, w, r2, x2, sum="add", mul=mul),
+            generalized_rspmm(ei, et, w, r2 ** 2, x2 ** 2, sum="add", mul=mul),
+            generalized_rspmm(ei, et, w, r2, x2, sum="max", mul=mul),
+            generalized_rspmm(ei, et, w, r2, x2, sum="min", mul=mul)]
+    sum((o * g_).sum() for o, g_ in zip(refs, ogs)).backward()
+    for name, a, b in zip(("sum", "sq_sum", "max", "min"), outs, refs):
+        if name in ("max", "min"):
+            assert_equal_values(a.detach(), b.detach().cpu(), name)
+        else:
+            assert_close_ref(a.detach(), b.detach().cpu(), name)
+    assert_close_ref(x1.grad, x2.grad.cpu(), "input_grad")
+    assert_close_ref(r1.grad, r2.grad.cpu(), "relation_grad")
+    # and against the oracle directly
+    for name, s_, a in (("sum", "add", outs[0]), ("max", "max", outs[2]), ("min", "min", outs[3])):
+        exp = oracle_all(s_, mul, ei.cpu(), et.cpu(), w.cpu(), rel, x)
+        (assert_close_ref if s_ == "add" else assert_equal_values)(a.detach(), exp, name + " vs oracle")

@@ -77,12 +77,14 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
 
     if (heads == 0 && !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary})) {
         if (boundary != nullptr) { set_error("boundary fusion needs the vector path (D % 4 == 0, aligned)"); return 1; }
+        if constexpr (SUM == S_PNA) { set_error("forward_pna needs the vector path (D % 4 == 0, aligned)"); return 1; } else {
         const long long total = (long long)so.num_seg * D;
         const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)plan->sm_count * 16);
         seg_reduce_generic_kernel<T, MODE, SUM, MUL><<<blocks, 256, 0, stream>>>(
             so.meta, w, so.seg_ptr, so.num_seg, relation, input, output, outgrad, dst, (int)D);
         CUDA_TRY(cudaGetLastError());
         return 0;
+        }
     }
 
     SegParams<T> p;
@@ -90,6 +92,8 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     p.num_warp_items = so.num_items / kSubPerWarp;
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
     p.dst = dst; p.partial = scratch; p.boundary = boundary; p.lay = lay;
+    p.dst_plane = (long long)plan->ord[MODE].num_seg * D;          // S_PNA: (4, N, D) outputs
+    p.partial_plane = (long long)plan->ord[MODE].num_slots * D;    // S_PNA: (4, slots, D) partials
     p.D = (int)D; p.R = (int)plan->R; p.N = (int)plan->N;
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
@@ -139,18 +143,33 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         CUDA_TRY(cudaGetLastError());
     }
     const int ncc = (int)((D + 32 * V - 1) / (32 * V));
-    if (so.num_fix_long > 0) {
-        fold_partials_kernel<T, Nd::red><<<so.num_fix_long * ncc, 256, 0, stream>>>(
-            so.fix, so.num_fix_long, scratch, dst, boundary, (int)D, lay, dst_grp_bytes);
-        CUDA_TRY(cudaGetLastError());
-    }
     const int num_empty = so.num_fix - so.num_fix_long;
-    if (num_empty > 0) {
-        const long long warps = (long long)num_empty * ncc;
-        const int blocks = (int)((warps * 32 + 255) / 256);
-        fill_identity_kernel<T, Nd::red><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst, boundary,
-                                                                     (int)D, lay, dst_grp_bytes);
-        CUDA_TRY(cudaGetLastError());
+    // one fold + one identity fill per accumulator plane (1, or 4 for S_PNA: sum, sum of squares, max, min)
+    auto fix_plane = [&](auto red_tag, int a) -> int {
+        constexpr int RED = decltype(red_tag)::value;
+        T *dst_a = dst + (size_t)a * p.dst_plane;
+        const T *part_a = scratch + (size_t)a * p.partial_plane;
+        if (so.num_fix_long > 0) {
+            fold_partials_kernel<T, RED><<<so.num_fix_long * ncc, 256, 0, stream>>>(
+                so.fix, so.num_fix_long, part_a, dst_a, boundary, (int)D, lay, dst_grp_bytes);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (num_empty > 0) {
+            const long long warps = (long long)num_empty * ncc;
+            const int blocks = (int)((warps * 32 + 255) / 256);
+            fill_identity_kernel<T, RED><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst_a,
+                                                                     boundary, (int)D, lay, dst_grp_bytes);
+            CUDA_TRY(cudaGetLastError());
+        }
+        return 0;
+    };
+    if constexpr (Nd::red == S_PNA) {
+        if (int rc = fix_plane(std::integral_constant<int, S_ADD>{}, 0)) return rc;
+        if (int rc = fix_plane(std::integral_constant<int, S_ADD>{}, 1)) return rc;
+        if (int rc = fix_plane(std::integral_constant<int, S_MAX>{}, 2)) return rc;
+        if (int rc = fix_plane(std::integral_constant<int, S_MIN>{}, 3)) return rc;
+    } else {
+        if (int rc = fix_plane(std::integral_constant<int, Nd::red>{}, 0)) return rc;
     }
     return 0;
 }
@@ -322,6 +341,23 @@ int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, i
                      input_grad, dim, scratch, stream)
     }
     return 1;
+}
+
+int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype, const void *relation,
+                            const void *input, void *output4, int64_t dim, void *scratch, size_t scratch_bytes_,
+                            void *stream_) {
+    if (int rc = check_common(plan, 0, mul_op, dtype, dim)) return rc;
+    if (scratch_bytes_ < 4 * scratch_bytes(plan, dim, dtype)) {
+        set_error("forward_pna: scratch too small (needs 4 x ultra_rspmm_scratch_bytes)");
+        return 1;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (dtype == ULTRA_RSPMM_F32) {
+        if (mul_op == 0) return forward_t<float, S_PNA, M_MUL>(plan, relation, input, output4, dim, scratch, stream);
+        return forward_t<float, S_PNA, M_ADD>(plan, relation, input, output4, dim, scratch, stream);
+    }
+    if (mul_op == 0) return forward_t<double, S_PNA, M_MUL>(plan, relation, input, output4, dim, scratch, stream);
+    return forward_t<double, S_PNA, M_ADD>(plan, relation, input, output4, dim, scratch, stream);
 }
 
 int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,

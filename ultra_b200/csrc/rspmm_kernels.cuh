@@ -40,7 +40,8 @@ constexpr int kCtaThreads = 512;
 constexpr int kCtaWarps = kCtaThreads / 32;
 
 enum { FWD = 0, BWD_IN = 1, BWD_REL = 2 };
-enum { S_ADD = 0, S_MIN = 1, S_MAX = 2 };
+enum { S_ADD = 0, S_MIN = 1, S_MAX = 2, S_PNA = 3 };  // S_PNA: forward only, 4 aggregates in one pass (sum, sum of
+                                                       // squares, max, min - the four rspmm calls of layers.py:211-215)
 enum { M_MUL = 0, M_ADD = 1 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -90,6 +91,19 @@ template <int SUM, typename T> __device__ __forceinline__ T nary_fwd(T r, T x) {
     if (SUM == S_MIN) return r < x ? r : x;
     return r > x ? r : x;
 }
+// accumulator a of a (possibly multi-aggregate) reduction: which Nary op it folds with
+__host__ __device__ constexpr int acc_count(int sum) { return sum == S_PNA ? 4 : 1; }
+__host__ __device__ constexpr int acc_op(int sum, int a) {
+    return sum != S_PNA ? sum : (a < 2 ? S_ADD : (a == 2 ? S_MAX : S_MIN));
+}
+template <typename T> __device__ __forceinline__ T nary_zero_dyn(int op) {
+    return op == S_ADD ? T(0) : (op == S_MIN ? Lim<T>::max() : -Lim<T>::max());
+}
+template <typename T> __device__ __forceinline__ T nary_fwd_dyn(int op, T r, T x) {
+    if (op == S_ADD) return r + x;
+    if (op == S_MIN) return r < x ? r : x;
+    return r > x ? r : x;
+}
 template <int SUM, typename T> __device__ __forceinline__ T nary_bwd(T r, T x) {  // operator.cuh:49,62,75
     if (SUM == S_ADD) return T(1);
     return r == x ? T(1) : T(0);
@@ -122,6 +136,8 @@ template <typename T> struct SegParams {
     const T *outgrad;   // (N, D)   backward only
     T *dst;             // output / input_grad / relation_grad
     T *partial;         // (num_slots, D), always flat
+    long long dst_plane;      // S_PNA: element stride between the 4 output matrices (sum, sq_sum, max, min)
+    long long partial_plane;  // S_PNA: element stride between the 4 partial buffers
     const T *boundary;  // forward only, optional: out = Nary(agg, boundary) (the NBFNet self-loop message); dst layout
     Layout lay;         // where tile t / row r of the feature matrices live (flat (rows, D) or head-major (B, rows, d))
     int D;
@@ -140,9 +156,10 @@ template <int MODE, int SUM, int MUL> struct Needs {
     static constexpr bool inb = (MODE == BWD_REL) && (MUL == M_MUL || SUM != S_ADD);   // input[b]
     static constexpr bool rel = (MODE == FWD) || (MODE == BWD_IN && (MUL == M_MUL || SUM != S_ADD));
     static constexpr bool self = (MODE != FWD) && (SUM != S_ADD);   // the segment's own input / relation row
-    static constexpr int red = (MODE == FWD) ? SUM : S_ADD;
+    static constexpr int red = (MODE == FWD) ? SUM : S_ADD;   // S_PNA: see acc_op()
+    static constexpr int nacc = acc_count(red);
     static constexpr int gathers = 1 + (out ? 1 : 0) + (inb ? 1 : 0);  // row slices fetched per edge
-    static constexpr int unroll = (gathers == 1 || (gathers == 2 && SUM == S_ADD)) ? 4 : 2;  // register budget: 64
+    static constexpr int unroll = (SUM != S_PNA && (gathers == 1 || (gathers == 2 && SUM == S_ADD))) ? 4 : 2;  // 64 regs
 };
 
 // shared-memory vector load through a 32-bit shared-window address (address math stays in 32 bits)
@@ -212,9 +229,14 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     // shared-window base (S2UR/ULEA) every iteration.
     asm volatile("" : "+l"(g1_c), "+l"(out_c), "+l"(in_c), "+l"(rel_c), "+r"(rel_q), "+r"(g1_q));
 
-    Vec<T> acc, self;
+    constexpr int NA = N::nacc;
+    Vec<T> acc[NA], self;
 #pragma unroll
-    for (int k = 0; k < V; k++) { acc.v[k] = nary_zero<N::red, T>(); self.v[k] = T(0); }
+    for (int a = 0; a < NA; a++)
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[a].v[k] = nary_zero_dyn<T>(acc_op(N::red, a));
+#pragma unroll
+    for (int k = 0; k < V; k++) self.v[k] = T(0);
     if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
 
     auto body = [&](auto pred_tag, int i) {
@@ -249,14 +271,24 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             }
         }
         auto consume = [&](int u) {
-            Vec<T> nxt;
+            Vec<T> nxt[NA];
 #pragma unroll
             for (int k = 0; k < V; k++) {
                 if (MODE == FWD) {
                     // rspmm.cu:68-70   x = Bin(rel, in); y = w * x; out = Nary(out, y)
                     T y = bin_fwd<MUL>(rr[u].v[k], g1[u].v[k]);
                     if (!UNITW) y = wv[u] * y;
-                    nxt.v[k] = nary_fwd<SUM>(acc.v[k], y);
+                    if (SUM == S_PNA) {
+                        // layers.py:211-215: sum, sum over (relation**2, input**2), max, min of the same messages
+                        T y2 = bin_fwd<MUL>(rr[u].v[k] * rr[u].v[k], g1[u].v[k] * g1[u].v[k]);
+                        if (!UNITW) y2 = wv[u] * y2;
+                        nxt[0].v[k] = acc[0].v[k] + y;
+                        nxt[NA > 1 ? 1 : 0].v[k] = acc[NA > 1 ? 1 : 0].v[k] + y2;
+                        nxt[NA > 2 ? 2 : 0].v[k] = acc[NA > 2 ? 2 : 0].v[k] > y ? acc[NA > 2 ? 2 : 0].v[k] : y;
+                        nxt[NA > 3 ? 3 : 0].v[k] = acc[NA > 3 ? 3 : 0].v[k] < y ? acc[NA > 3 ? 3 : 0].v[k] : y;
+                    } else {
+                        nxt[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], y);
+                    }
                 } else if (MODE == BWD_IN) {
                     // rspmm.cu:198-209  input_grad[col] += og * dout_dy * w * dx_din ; segment = col
                     T g = g1[u].v[k];
@@ -267,7 +299,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                     }
                     if (!UNITW) g = g * wv[u];
                     if (MUL == M_MUL) g = g * rr[u].v[k];
-                    nxt.v[k] = acc.v[k] + g;
+                    nxt[0].v[k] = acc[0].v[k] + g;
                 } else {
                     // rspmm.cu:198-208  relation_grad[type] += og * dout_dy * w * dx_drel ; segment = type
                     T g = g1[u].v[k];
@@ -278,11 +310,13 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                     }
                     if (!UNITW) g = g * wv[u];
                     if (MUL == M_MUL) g = g * g3[u].v[k];
-                    nxt.v[k] = acc.v[k] + g;
+                    nxt[0].v[k] = acc[0].v[k] + g;
                 }
             }
 #pragma unroll
-            for (int k = 0; k < V; k++) acc.v[k] = ok[u] ? nxt.v[k] : acc.v[k];
+            for (int a = 0; a < NA; a++)
+#pragma unroll
+                for (int k = 0; k < V; k++) acc[a].v[k] = ok[u] ? nxt[a].v[k] : acc[a].v[k];
         };
         // one row-end test for the whole group of U edges (row ends are rare: the common path is pure FMA)
         int any = 0;
@@ -298,15 +332,20 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                 // segment end inside a whole-segment item: emit the finished row, start the next one
                 if (m[u].y < 0 && ok[u]) {
                     if (st_ok) {
-                        if (has_bnd) {
+                        if (has_bnd && NA == 1) {
                             const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
 #pragma unroll
-                            for (int k = 0; k < V; k++) acc.v[k] = nary_fwd<N::red>(acc.v[k], bv.v[k]);
+                            for (int k = 0; k < V; k++) acc[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], bv.v[k]);
                         }
-                        st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes), acc);
+#pragma unroll
+                        for (int a = 0; a < NA; a++)
+                            st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes) +
+                                          (size_t)a * p.dst_plane, acc[a]);
                     }
 #pragma unroll
-                    for (int k = 0; k < V; k++) acc.v[k] = nary_zero<N::red, T>();
+                    for (int a = 0; a < NA; a++)
+#pragma unroll
+                        for (int k = 0; k < V; k++) acc[a].v[k] = nary_zero_dyn<T>(acc_op(N::red, a));
                     j++;
                     seg = (unsigned)__ldg(p.nonempty + j);  // padded by one entry (0): always a valid row
                     if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
@@ -322,12 +361,21 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
 #pragma unroll
         for (int off = kLanesPerEdge; off < 32; off <<= 1) {
 #pragma unroll
-            for (int k = 0; k < V; k++)
-                acc.v[k] = nary_fwd<N::red>(acc.v[k], __shfl_xor_sync(0xffffffffu, acc.v[k], off));
+            for (int a = 0; a < NA; a++)
+#pragma unroll
+                for (int k = 0; k < V; k++)
+                    acc[a].v[k] = nary_fwd_dyn<T>(acc_op(N::red, a), acc[a].v[k],
+                                                  __shfl_xor_sync(0xffffffffu, acc[a].v[k], off));
         }
-        if (sg == 0 && st_ok) st_plain(p.partial + (size_t)slot * p.D + c0, acc);
+        if (sg == 0 && st_ok) {
+#pragma unroll
+            for (int a = 0; a < NA; a++)
+                st_plain(p.partial + (size_t)a * p.partial_plane + (size_t)slot * p.D + c0, acc[a]);
+        }
     } else if (slot >= 0 && st_ok) {  // single chunk of a long segment
-        st_plain(p.partial + (size_t)slot * p.D + c0, acc);
+#pragma unroll
+        for (int a = 0; a < NA; a++)
+            st_plain(p.partial + (size_t)a * p.partial_plane + (size_t)slot * p.D + c0, acc[a]);
     }
 }
 
