@@ -49,6 +49,16 @@ const char *ultra_rspmm_version(void);
 int ultra_rspmm_set_tunable(const char *name, int value);
 int ultra_rspmm_get_sm_limit(void);
 
+/*
+ * Host-only (no GPU needed): run the plan's work-item cutter on a CSR segment pointer (num_seg + 1 ints) and return
+ * items (int4 {e_begin, e_end, j0 | merged_bit(1<<30), slot}), the fix list (int4 {segment, slot_begin, slot_count, 0};
+ * the first num_fix_long entries are long segments, the rest empty ones) and the non-empty segment ids.  Exists so
+ * that the CPU test-suite can check the partition invariants; not used by the product path.
+ */
+int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items,
+                                int *fix_out, int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots,
+                                int *nonempty_out, int64_t nonempty_cap, int *num_nonempty);
+
 /* Message of the last failing call on this thread ("" if none). */
 const char *ultra_rspmm_last_error(void);
 

@@ -252,6 +252,17 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
 
 int ultra_rspmm_get_sm_limit(void) { return g_sm_limit.load(); }
 
+int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items,
+                                int *fix_out, int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots,
+                                int *nonempty_out, int64_t nonempty_cap, int *num_nonempty) {
+    if (!seg_ptr || num_seg < 0 || !num_items || !num_fix || !num_fix_long || !num_slots || !num_nonempty) {
+        set_error("debug_cut_items: bad arguments");
+        return 1;
+    }
+    return cut_items_host(seg_ptr, num_seg, items_out, items_cap, num_items, fix_out, fix_cap, num_fix, num_fix_long,
+                          num_slots, nonempty_out, nonempty_cap, num_nonempty);
+}
+
 const char *ultra_rspmm_last_error(void) { return g_last_error.c_str(); }
 
 size_t ultra_rspmm_plan_workspace_bytes(int64_t num_node, int64_t num_edge, int64_t num_relation) {

@@ -178,6 +178,27 @@ void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vecto
 
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layout(N, E, R).total; }
 
+// Host-only access to the work-item cutter (pure CPU; used by the CPU test-suite to check its invariants).
+int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
+                   int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
+                   int64_t nonempty_cap, int *num_nonempty) {
+    std::vector<int> ptr(seg_ptr, seg_ptr + num_seg + 1);
+    std::vector<int4> items, fix;
+    std::vector<int> nonempty;
+    int slots = 0, nlong = 0;
+    cut_items(ptr, items, nonempty, fix, slots, nlong);
+    if ((int64_t)items.size() > items_cap || (int64_t)fix.size() > fix_cap || (int64_t)nonempty.size() > nonempty_cap) {
+        set_error("cut_items_host: output capacity too small");
+        return 1;
+    }
+    if (!items.empty()) std::memcpy(items_out, items.data(), items.size() * sizeof(int4));
+    if (!fix.empty()) std::memcpy(fix_out, fix.data(), fix.size() * sizeof(int4));
+    if (!nonempty.empty()) std::memcpy(nonempty_out, nonempty.data(), nonempty.size() * sizeof(int));
+    *num_items = (int)items.size(); *num_fix = (int)fix.size(); *num_fix_long = nlong; *num_slots = slots;
+    *num_nonempty = (int)nonempty.size();
+    return 0;
+}
+
 int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t *edge_type, int64_t N, int64_t E,
                int64_t R, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (N < 0 || E < 0 || R < 0 || N >= (int64_t(1) << 30) || E >= (int64_t(1) << 31) - 64 ||

@@ -43,6 +43,9 @@ struct ultra_rspmm_plan {
 namespace ultra {
 void set_error(const std::string &msg);
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
+int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
+                   int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
+                   int64_t nonempty_cap, int *num_nonempty);
 int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t *edge_type, int64_t N, int64_t E,
                int64_t R, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace ultra
