@@ -26,7 +26,8 @@ namespace {
         }                                                                                      \
     } while (0)
 
-constexpr size_t kSlabSmemLimit = 100 * 1024;
+constexpr size_t kMetaSmem = (size_t)kCtaWarps * kMetaStageBytes;  // 32 KB of per-warp metadata staging per CTA
+constexpr size_t kSlabSmemLimit = 78 * 1024;  // tiles in smem while 2 CTAs/SM (tiles + metadata + reserve) still fit in 227 KB
 
 // process-wide launch tunables (ultra_rspmm_set_tunable)
 std::atomic<int> g_sm_limit{0};          // 0 = use every SM; >0 = size persistent grids for this many SMs
@@ -130,15 +131,16 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         else if (Nd::rel && rel_bytes <= kSlabSmemLimit) sm_mode = 1;
         auto launch = [&](auto kern, size_t smem) -> int {
             if (smem > 48 * 1024) {  // opt-in above 48 KB; cudaFuncSetAttribute is cheap and idempotent
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSlabSmemLimit));
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(kSlabSmemLimit + kMetaSmem)));
             }
             kern<<<grid, kCtaThreads, smem, stream>>>(p);
             return 0;
         };
         int lrc = 0;
-        if (sm_mode == 2) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 2>, rel_bytes + g1_bytes);
-        else if (sm_mode == 1) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 1>, rel_bytes);
-        else lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 0>, 0);
+        if (sm_mode == 2) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 2>, rel_bytes + g1_bytes + kMetaSmem);
+        else if (sm_mode == 1) lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 1>, rel_bytes + kMetaSmem);
+        else lrc = launch(seg_reduce_kernel<T, MODE, SUM, MUL, 0>, kMetaSmem);
         if (lrc) return lrc;
         CUDA_TRY(cudaGetLastError());
     }
