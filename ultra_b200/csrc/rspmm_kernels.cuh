@@ -19,7 +19,8 @@
 // at once with no cross-lane traffic.  CTAs are persistent and walk (tile, item-chunk) units TILE-MAJOR so
 // that the concurrently active tiles of `input` (N x 128 B each) stay L2-resident: HBM sees ~compulsory
 // traffic and the gathers are served by L2.  The relation tile (R x 128 B) is staged in shared memory once per
-// (CTA, tile) visit by TMA bulk copies (cp.async.bulk, one 128-byte row slice each, mbarrier completion).  The
+// (CTA, tile) visit, each warp stages its items' metadata in shared memory (coalesced loads, broadcast LDS in the loop),
+// and the relation tile is brought in by TMA bulk copies (cp.async.bulk, one 128-byte row slice each, mbarrier completion).  The
 // per-edge gathers themselves stay LDG.128 -> registers: tools/gather_microbench.cu measures 128-byte TMA bulk
 // gathers at <= the LDG rate (both ~7 TB/s, the L2 limit) while costing an smem round trip and the L1 hits.
 #pragma once
