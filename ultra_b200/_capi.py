@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libultra_rspmm.so")
+LIB_PATH = os.environ.get("ULTRA_RSPMM_LIB") or os.path.join(_HERE, "lib", "libultra_rspmm.so")  # env: dev A/B builds
 
 SUM_IDS = {"add": 0, "min": 1, "max": 2}
 MUL_IDS = {"mul": 0, "add": 1}

@@ -32,6 +32,9 @@
 
 namespace ultra {
 
+#ifndef ULTRA_FWD_UNROLL
+#define ULTRA_FWD_UNROLL 4  // edges per lane in flight in the single-gather passes (register budget: 64/thread)
+#endif
 constexpr int kLanesPerEdge = 8;
 constexpr int kSubPerWarp = 32 / kLanesPerEdge;  // 4 items walked concurrently by one warp
 constexpr int kTileBytes = 128;
@@ -161,7 +164,7 @@ template <int MODE, int SUM, int MUL> struct Needs {
     static constexpr int red = (MODE == FWD) ? SUM : S_ADD;   // S_PNA: see acc_op()
     static constexpr int nacc = acc_count(red);
     static constexpr int gathers = 1 + (out ? 1 : 0) + (inb ? 1 : 0);  // row slices fetched per edge
-    static constexpr int unroll = (SUM != S_PNA && (gathers == 1 || (gathers == 2 && SUM == S_ADD))) ? 4 : 2;  // 64 regs
+    static constexpr int unroll = (SUM != S_PNA && gathers == 1) ? ULTRA_FWD_UNROLL : ((SUM != S_PNA && gathers == 2 && SUM == S_ADD) ? 4 : 2);  // 64 regs
 };
 
 // shared-memory vector load through a 32-bit shared-window address (address math stays in 32 bits)
@@ -265,7 +268,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             int k = i + u;
             ok[u] = true;
             if (PRED) { ok[u] = k < len; k = k < len ? k : len_m1; }
-            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(m[u].x), "=r"(m[u].y) : "r"(my_meta + (uint32_t)(i + u) * 8u));
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(m[u].x), "=r"(m[u].y) : "r"(my_meta + (uint32_t)k * 8u));
             wv[u] = T(1);
             if (!UNITW) wv[u] = __ldg(wp + k);
         }
@@ -278,15 +281,15 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             if (N::inb) g3[u] = ld_row<T>(in_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
         }
         Vec<T> rr[U];
-        if (N::rel) {
+        if (N::rel && !REL_SMEM) {  // relation rows from L1/L2: issue all loads up front (long latency)
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
-                if (REL_SMEM) rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
-                else rr[u] = ld_row<T>(rel_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
-            }
+            for (int u = 0; u < U; u++) rr[u] = ld_row<T>(rel_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
         }
         auto consume = [&](int u) {
+            // relation tile in shared memory: fetch the vector just in time (~30 cycles, other warps cover it) instead
+            // of holding U of them in registers - the registers are better spent on row gathers in flight.
+            // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
+            if (N::rel && REL_SMEM) rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
             Vec<T> nxt[NA];
 #pragma unroll
             for (int k = 0; k < V; k++) {
