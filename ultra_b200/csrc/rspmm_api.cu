@@ -31,7 +31,8 @@ constexpr size_t kSlabSmemLimit = 78 * 1024;  // tiles in smem while 2 CTAs/SM (
 
 // process-wide launch tunables (ultra_rspmm_set_tunable)
 std::atomic<int> g_sm_limit{0};          // 0 = use every SM; >0 = size persistent grids for this many SMs
-std::atomic<int> g_l2_percent{25};       // share of L2 the concurrently gathered tiles may occupy  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
+std::atomic<int> g_l2_percent{25};
+std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy       // share of L2 the concurrently gathered tiles may occupy  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
 
 template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
     if (D % VecN<T>::value != 0) return false;
@@ -247,8 +248,9 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (name == nullptr) { set_error("set_tunable: null name"); return 1; }
     const std::string n(name);
     if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
+    if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent)");
+    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split)");
     return 1;
 }
 
@@ -445,62 +447,101 @@ int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_o
         buf[b].out = p; p += up(N * slab_dim * es);
         buf[b].scr = p;
     }
-    // three lanes: copy-in, compute, copy-out; events chain them per slab and protect buffer reuse
-    cudaStream_t s_in, s_k, s_out;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    cudaEvent_t ev_start, ev_in[2], ev_k[2], ev_out[2], ev_done;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
-    for (int b = 0; b < 2; b++) {
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
+    // lanes: copy-in (x split), compute, copy-out (x split); events chain them per slab and protect buffer reuse.
+    // `split` > 1 issues each slab copy as `split` row blocks on separate streams so that more than one copy engine
+    // works on the strided (2 KB per row) transfers.
+    constexpr int kMax = 4;
+    struct Lanes {  // RAII: every exit path releases the streams / events (pending work completes first)
+        cudaStream_t in[kMax] = {}, out[kMax] = {}, k = nullptr;
+        cudaEvent_t start = nullptr, done = nullptr, ein[2][kMax] = {}, ek[2] = {}, eout[2][kMax] = {};
+        ~Lanes() {
+            for (int i = 0; i < kMax; i++) {
+                if (in[i]) cudaStreamDestroy(in[i]);
+                if (out[i]) cudaStreamDestroy(out[i]);
+                for (int b = 0; b < 2; b++) {
+                    if (ein[b][i]) cudaEventDestroy(ein[b][i]);
+                    if (eout[b][i]) cudaEventDestroy(eout[b][i]);
+                }
+            }
+            if (k) cudaStreamDestroy(k);
+            if (start) cudaEventDestroy(start);
+            if (done) cudaEventDestroy(done);
+            for (int b = 0; b < 2; b++) if (ek[b]) cudaEventDestroy(ek[b]);
+        }
+    } L;
+    const int split = std::max(1, std::min(g_host_copy_split.load(), kMax));
+    CUDA_TRY(cudaStreamCreateWithFlags(&L.k, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&L.start, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&L.ek[b], cudaEventDisableTiming));
+    for (int i = 0; i < split; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.in[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&L.out[i], cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&L.ein[b][i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&L.eout[b][i], cudaEventDisableTiming));
+        }
     }
-    CUDA_TRY(cudaEventRecord(ev_start, stream));
-    CUDA_TRY(cudaStreamWaitEvent(s_in, ev_start, 0));
-    CUDA_TRY(cudaStreamWaitEvent(s_k, ev_start, 0));
-    CUDA_TRY(cudaStreamWaitEvent(s_out, ev_start, 0));
+    CUDA_TRY(cudaEventRecord(L.start, stream));
+    CUDA_TRY(cudaStreamWaitEvent(L.k, L.start, 0));
+    for (int i = 0; i < split; i++) {
+        CUDA_TRY(cudaStreamWaitEvent(L.in[i], L.start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(L.out[i], L.start, 0));
+    }
+    auto rows_of = [&](size_t total, int i, size_t &r0, size_t &cnt) {
+        const size_t per = (total + split - 1) / split;
+        r0 = std::min(total, per * i);
+        cnt = std::min(total - r0, per);
+    };
     int rc = 0;
     int it = 0;
     for (int64_t c0 = 0; c0 < dim && rc == 0; c0 += slab_dim, it++) {
         const int b = it & 1;
         const int64_t wd = std::min(slab_dim, dim - c0);
         const size_t wbytes = (size_t)wd * es, pitch_h = (size_t)dim * es;
-        if (it >= 2) {  // buffer b: its previous kernel must be done before H2D overwrites rel/in,
-            CUDA_TRY(cudaStreamWaitEvent(s_in, ev_k[b], 0));  // and its previous D2H before the kernel rewrites out
+        for (int i = 0; i < split; i++) {
+            // buffer b: its previous kernel must be done before H2D overwrites rel / in
+            if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(L.in[i], L.ek[b], 0));
+            size_t r0, cnt;
+            rows_of(R, i, r0, cnt);
+            if (cnt > 0)
+                CUDA_TRY(cudaMemcpy2DAsync(buf[b].rel + r0 * wbytes, wbytes,
+                                           (const char *)h_relation + r0 * pitch_h + c0 * es, pitch_h, wbytes, cnt,
+                                           cudaMemcpyHostToDevice, L.in[i]));
+            rows_of(N, i, r0, cnt);
+            if (cnt > 0)
+                CUDA_TRY(cudaMemcpy2DAsync(buf[b].in + r0 * wbytes, wbytes,
+                                           (const char *)h_input + r0 * pitch_h + c0 * es, pitch_h, wbytes, cnt,
+                                           cudaMemcpyHostToDevice, L.in[i]));
+            CUDA_TRY(cudaEventRecord(L.ein[b][i], L.in[i]));
+            CUDA_TRY(cudaStreamWaitEvent(L.k, L.ein[b][i], 0));
+            // ... and its previous D2H before the kernel rewrites out
+            if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(L.k, L.eout[b][i], 0));
         }
-        if (R > 0)
-            CUDA_TRY(cudaMemcpy2DAsync(buf[b].rel, wbytes, (const char *)h_relation + c0 * es, pitch_h, wbytes, R,
-                                       cudaMemcpyHostToDevice, s_in));
-        if (N > 0)
-            CUDA_TRY(cudaMemcpy2DAsync(buf[b].in, wbytes, (const char *)h_input + c0 * es, pitch_h, wbytes, N,
-                                       cudaMemcpyHostToDevice, s_in));
-        CUDA_TRY(cudaEventRecord(ev_in[b], s_in));
-        CUDA_TRY(cudaStreamWaitEvent(s_k, ev_in[b], 0));
-        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(s_k, ev_out[b], 0));
         rc = ultra_rspmm_forward(plan, sum_op, mul_op, dtype, buf[b].rel, buf[b].in, buf[b].out, wd, buf[b].scr,
-                                 sb, s_k);
+                                 sb, L.k);
         if (rc) break;
-        CUDA_TRY(cudaEventRecord(ev_k[b], s_k));
-        CUDA_TRY(cudaStreamWaitEvent(s_out, ev_k[b], 0));
-        if (N > 0)
-            CUDA_TRY(cudaMemcpy2DAsync((char *)h_output + c0 * es, pitch_h, buf[b].out, wbytes, wbytes, N,
-                                       cudaMemcpyDeviceToHost, s_out));
-        CUDA_TRY(cudaEventRecord(ev_out[b], s_out));
+        CUDA_TRY(cudaEventRecord(L.ek[b], L.k));
+        for (int i = 0; i < split; i++) {
+            CUDA_TRY(cudaStreamWaitEvent(L.out[i], L.ek[b], 0));
+            size_t r0, cnt;
+            rows_of(N, i, r0, cnt);
+            if (cnt > 0)
+                CUDA_TRY(cudaMemcpy2DAsync((char *)h_output + r0 * pitch_h + c0 * es, pitch_h,
+                                           buf[b].out + r0 * wbytes, wbytes, wbytes, cnt, cudaMemcpyDeviceToHost,
+                                           L.out[i]));
+            CUDA_TRY(cudaEventRecord(L.eout[b][i], L.out[i]));
+        }
     }
-    // join the three lanes back into the caller's stream
-    CUDA_TRY(cudaEventRecord(ev_done, s_in));
-    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
-    CUDA_TRY(cudaEventRecord(ev_done, s_k));
-    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
-    CUDA_TRY(cudaEventRecord(ev_done, s_out));
-    CUDA_TRY(cudaStreamWaitEvent(stream, ev_done, 0));
-    // destroying streams/events with pending work is legal: resources are released when the work completes
-    cudaEventDestroy(ev_start); cudaEventDestroy(ev_done);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_k[b]); cudaEventDestroy(ev_out[b]); }
-    cudaStreamDestroy(s_in); cudaStreamDestroy(s_k); cudaStreamDestroy(s_out);
+    // join every lane back into the caller's stream
+    CUDA_TRY(cudaEventRecord(L.done, L.k));
+    CUDA_TRY(cudaStreamWaitEvent(stream, L.done, 0));
+    for (int i = 0; i < split; i++) {
+        CUDA_TRY(cudaEventRecord(L.done, L.in[i]));
+        CUDA_TRY(cudaStreamWaitEvent(stream, L.done, 0));
+        CUDA_TRY(cudaEventRecord(L.done, L.out[i]));
+        CUDA_TRY(cudaStreamWaitEvent(stream, L.done, 0));
+    }
     return rc;
 }
 
