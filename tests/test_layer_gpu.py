@@ -215,3 +215,24 @@ def test_fused_layer_matches_restatement(cuda_device, message, aggregate):
             torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
     finally:
         GeneralizedRelationalConv.fuse = True
+
+
+def test_graphed_bellmanford_matches_eager(cuda_device):
+    """6-layer stack captured as one CUDA graph == the eager loop, for fresh inputs after capture."""
+    from ultra_b200.layer import GeneralizedRelationalConv, bellmanford_entity, GraphedBellmanFord
+    torch.manual_seed(4)
+    dev = cuda_device
+    B, N, R, d, E = 4, 150, 4, 64, 6000
+    layers = [GeneralizedRelationalConv(d, d, R, d, "distmult", "sum", layer_norm=True).to(dev) for _ in range(6)]
+    ei = torch.randint(0, N, (2, E), device=dev)
+    et = torch.randint(0, R, (E,), device=dev)
+    q0, h0 = torch.randn(B, d, device=dev), torch.randint(0, N, (B,), device=dev)
+    graphed = GraphedBellmanFord(layers, q0, h0, ei, et, N)
+    for seed in (1, 2, 3):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        q = torch.randn(B, d, device=dev, generator=g)
+        h = torch.randint(0, N, (B,), device=dev, generator=g)
+        with torch.no_grad():
+            eager = bellmanford_entity(layers, q, h, ei, et, N)
+        out = graphed(q, h)
+        assert torch.equal(out, eager)
