@@ -221,7 +221,10 @@ int check_common(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype
     if (plan == nullptr) { set_error("null plan"); return 1; }
     if (sum_op < 0 || sum_op > 2 || mul_op < 0 || mul_op > 1) { set_error("unknown sum_op / mul_op"); return 1; }
     if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) { set_error("unknown dtype"); return 1; }
-    if (dim < 0 || dim >= (int64_t(1) << 31)) { set_error("dim out of range"); return 1; }
+    if (dim < 0 || dim >= (int64_t(1) << 31) || dim * (dtype == ULTRA_RSPMM_F32 ? 4 : 8) >= (int64_t(1) << 32)) {
+        set_error("dim out of range (a feature row must be shorter than 4 GiB)");
+        return 1;
+    }
     if (!plan->unit_weight && plan->w_dtype != dtype) {
         set_error("edge weights were bound with a different dtype than relation/input (checkAllSameType)");
         return 1;

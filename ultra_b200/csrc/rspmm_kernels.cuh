@@ -18,11 +18,12 @@
 // tile slice (one 16-byte vector load per lane, a full 128-byte L2 line per edge), so a warp walks 4 items
 // at once with no cross-lane traffic.  CTAs are persistent and walk (tile, item-chunk) units TILE-MAJOR so
 // that the concurrently active tiles of `input` (N x 128 B each) stay L2-resident: HBM sees ~compulsory
-// traffic and the gathers are served by L2.  The relation tile (R x 128 B) is staged in shared memory once per
-// (CTA, tile) visit, each warp stages its items' metadata in shared memory (coalesced loads, broadcast LDS in the loop),
-// and the relation tile is brought in by TMA bulk copies (cp.async.bulk, one 128-byte row slice each, mbarrier completion).  The
-// per-edge gathers themselves stay LDG.128 -> registers: tools/gather_microbench.cu measures 128-byte TMA bulk
-// gathers at <= the LDG rate (both ~7 TB/s, the L2 limit) while costing an smem round trip and the L1 hits.
+// traffic and the gathers are served by L2/L1.  Shared memory holds, per CTA: the relation tile (R x 128 B, staged
+// once per (CTA, tile) visit by TMA bulk copies - cp.async.bulk, one 128-byte row slice each, mbarrier completion),
+// for small graphs also the gathered matrix' tile (N x 128 B), and each warp's item metadata (coalesced loads at item
+// start, broadcast LDS in the loop).  The per-edge gathers themselves stay LDG.128 -> registers:
+// tools/gather_microbench.cu measures 128-byte TMA bulk gathers at <= the LDG rate (both ~7 TB/s, the L2 limit) while
+// costing an smem round trip and the L1 hits.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -64,9 +65,6 @@ template <typename T> __device__ __forceinline__ Vec<T> ld_gather(const T *p) { 
         r.v[0] = t.x; r.v[1] = t.y;
     }
     return r;
-}
-template <typename T> __device__ __forceinline__ Vec<T> ld_shared(const T *p) {
-    return *reinterpret_cast<const Vec<T> *>(p);
 }
 template <typename T> __device__ __forceinline__ void st_stream(T *p, const Vec<T> &x) {  // evict-first store
     if constexpr (sizeof(T) == 4) {
