@@ -368,6 +368,12 @@ def bench_layer(wl, device, world, rank):
                 return g.wait()
             info["stack6_ms_with_per_layer_allgather"] = timeit(stack_gather, reps=3, warm=1)
             info["allgather_bytes_per_layer_per_gpu"] = 4 * B * world * N * d
+
+            def stack_gather_last():  # what a scorer needs: only the final layer's states, replicated
+                g = OverlappedStateGather(B * world, layers=[len(layers) - 1])
+                bellmanford_entity(layers, query, h_index, ei, et, N, hook=g.after_layer)
+                return g.wait()
+            info["stack6_ms_with_final_allgather"] = timeit(stack_gather_last, reps=3, warm=1)
     del layers, x, bd
     torch.cuda.empty_cache()
     return info
