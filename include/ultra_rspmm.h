@@ -45,6 +45,8 @@ const char *ultra_rspmm_version(void);
  * Process-wide launch tunables.  "sm_limit": size the persistent grids for this many SMs (0 = all) so that a
  * concurrent NCCL collective (the overlapped all-gather of node states, ultra_b200/shard.py) finds free SMs.
  * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
+ * "update_impl": 0 (default) runs ultra_nbfnet_update_f32 on the tensor cores (tcgen05, 3xTF32 split, fp32-level
+ * accuracy), 1 selects the plain fp32 FFMA kernel.  "host_copy_split": row blocks per slab copy in forward_host.
  */
 int ultra_rspmm_set_tunable(const char *name, int value);
 int ultra_rspmm_get_sm_limit(void);

@@ -147,10 +147,13 @@ def test_rspmm_heads_equals_flat_path(cuda_device, sum, mul, dtype, d, with_boun
         assert torch.equal(b1.grad, b2.grad)
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05_3xtf32", "ffma"])
 @pytest.mark.parametrize("layer_norm,relu,shortcut", [(True, True, True), (True, True, False), (False, True, True),
                                                       (True, False, False)])
-def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut):
+def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
+    from ultra_b200 import _capi
     from ultra_b200.fused import nbfnet_update
+    _capi.set_tunable("update_impl", impl)
     dev = cuda_device
     torch.manual_seed(5)
     lin = torch.nn.Linear(128, 64).to(dev)
@@ -172,6 +175,7 @@ def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut):
             if shortcut:
                 ref = ref + x.double()
         torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=2e-5)
+    _capi.set_tunable("update_impl", 0)
 
 
 @pytest.mark.parametrize("message,aggregate", [("distmult", "sum"), ("transe", "max"), ("distmult", "mean")])

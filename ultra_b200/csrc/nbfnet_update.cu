@@ -18,8 +18,16 @@
 
 #include "../../include/ultra_rspmm.h"
 
+#include <atomic>
+
 namespace ultra {
 void set_error(const std::string &msg);
+// tensor-core (tcgen05, 3xTF32) implementation, nbfnet_update_tc.cu
+int launch_update_tc(const float *x, const float *u, const float *weight_t, const float *bias, const float *gamma,
+                     const float *beta, float *out, int64_t num_rows, float eps, int layer_norm, int relu, int shortcut,
+                     int sms, cudaStream_t stream);
+static std::atomic<int> g_update_impl{0};  // 0 = tensor cores (default), 1 = fp32 FFMA kernel of this file
+void set_update_impl(int v) { g_update_impl.store(v); }
 
 namespace {
 
@@ -162,6 +170,9 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
     if (err != cudaSuccess) { set_error(std::string("nbfnet_update: ") + cudaGetErrorString(err)); return 2; }
     const int sm_limit = ultra_rspmm_get_sm_limit();
     if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
+    if (g_update_impl.load() == 0)
+        return launch_update_tc(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,
+                                sms, stream);
     const long long tiles = (num_rows + kBM - 1) / kBM;
     const int grid = (int)(tiles < 2LL * sms ? tiles : 2LL * sms);
     nbfnet_update_kernel<<<grid, kThreads, kSmemBytes, stream>>>(x, u, weight_t, bias, ln_gamma, ln_beta, out,

@@ -251,9 +251,10 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (name == nullptr) { set_error("set_tunable: null name"); return 1; }
     const std::string n(name);
     if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
+    if (n == "update_impl") { set_update_impl(value); return 0; }
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split)");
+    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl)");
     return 1;
 }
 
