@@ -14,7 +14,6 @@ that are visible to a caller, all deliberate:
   * weight_grad is None instead of a zeros tensor when edge_weight does not require grad (the reference's CUDA
     path returns zeros that autograd then discards, rspmm.cu:295,312-331).
 """
-import ctypes
 import os
 import sys
 import threading
@@ -23,7 +22,7 @@ import torch
 from torch import autograd
 
 from .. import _capi
-from ..plan import GraphPlan, plan_cache, _DTYPE_ID, _stream_ptr
+from ..plan import plan_cache, _DTYPE_ID, _stream_ptr
 
 module = sys.modules[__name__]
 
