@@ -82,8 +82,12 @@ def main():
                                                   og.data_ptr(), None, rg.data_ptr(), ig.data_ptr(), D,
                                                   scratch.data_ptr(), scratch.numel(), _stream_ptr(d))
                     assert rc == 0, lib.ultra_rspmm_last_error()
-                med, best = time_fn(bwd, iters=5)
-                print(json.dumps({"op": op, "pass": "bwd", "alpha": alpha, "ms_med": round(med, 4), "ms_min": round(best, 4)}))
+                for fused in (0, 1):
+                    _capi.set_tunable("bwd_fused_relgrad", fused)
+                    med, best = time_fn(bwd, iters=5)
+                    print(json.dumps({"op": op, "pass": "bwd", "fused_relgrad": fused, "alpha": alpha,
+                                      "ms_med": round(med, 4), "ms_min": round(best, 4)}))
+                _capi.set_tunable("bwd_fused_relgrad", 0)
         del plan
 
 

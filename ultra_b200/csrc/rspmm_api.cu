@@ -31,8 +31,9 @@ constexpr size_t kSlabSmemLimit = 78 * 1024;  // tiles in smem while 2 CTAs/SM (
 
 // process-wide launch tunables (ultra_rspmm_set_tunable)
 std::atomic<int> g_sm_limit{0};          // 0 = use every SM; >0 = size persistent grids for this many SMs
-std::atomic<int> g_l2_percent{25};
-std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy       // share of L2 the concurrently gathered tiles may occupy  // relation tile in smem while 2 CTAs/SM still fit (227 KB/SM)
+std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
+std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy
+std::atomic<int> g_bwd_fused_relgrad{0}; // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
 
 template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
     if (D % VecN<T>::value != 0) return false;
@@ -46,9 +47,10 @@ template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *>
 template <typename T, int MODE, int SUM, int MUL>
 int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input, const T *output,
                 const T *outgrad, T *dst, T *scratch, int64_t D, cudaStream_t stream, int64_t heads = 0,
-                const T *boundary = nullptr) {
+                const T *boundary = nullptr, T *rgrad = nullptr) {
     using Nd = Needs<MODE, SUM, MUL>;
-    const SegOrder &so = plan->ord[MODE];
+    constexpr int ORD = order_of(MODE);  // BWD_BOTH walks the by-column order
+    const SegOrder &so = plan->ord[ORD];
     const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
     if (so.num_seg == 0 || D == 0) return 0;
 
@@ -77,7 +79,8 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     }
     const long long dst_grp_bytes = MODE == BWD_REL ? lay.grp_rel_bytes : lay.grp_node_bytes;
 
-    if (heads == 0 && !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary})) {
+    if (heads == 0 && !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary, rgrad})) {
+        if constexpr (MODE == BWD_BOTH) { set_error("fused backward needs the vector path"); return 1; } else {
         if (boundary != nullptr) { set_error("boundary fusion needs the vector path (D % 4 == 0, aligned)"); return 1; }
         if constexpr (SUM == S_PNA) { set_error("forward_pna needs the vector path (D % 4 == 0, aligned)"); return 1; } else {
         const long long total = (long long)so.num_seg * D;
@@ -87,15 +90,16 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         CUDA_TRY(cudaGetLastError());
         return 0;
         }
+        }
     }
 
     SegParams<T> p;
     p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.nonempty = so.nonempty; p.items = so.items;
     p.num_warp_items = so.num_items / kSubPerWarp;
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
-    p.dst = dst; p.partial = scratch; p.boundary = boundary; p.lay = lay;
-    p.dst_plane = (long long)plan->ord[MODE].num_seg * D;          // S_PNA: (4, N, D) outputs
-    p.partial_plane = (long long)plan->ord[MODE].num_slots * D;    // S_PNA: (4, slots, D) partials
+    p.dst = dst; p.rgrad = rgrad; p.partial = scratch; p.boundary = boundary; p.lay = lay;
+    p.dst_plane = (long long)plan->ord[ORD].num_seg * D;          // S_PNA: (4, N, D) outputs
+    p.partial_plane = (long long)plan->ord[ORD].num_slots * D;    // S_PNA: (4, slots, D) partials
     p.D = (int)D; p.R = (int)plan->R; p.N = (int)plan->N;
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
@@ -188,12 +192,24 @@ template <typename T, int SUM, int MUL>
 int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, const void *output,
                const void *outgrad, void *wgrad, void *rgrad, void *igrad, int64_t D, void *scratch,
                cudaStream_t stream, int64_t heads = 0) {
-    int rc = launch_pass<T, BWD_IN, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
+    int rc;
+    const bool fused = g_bwd_fused_relgrad.load() != 0 && plan->R > 0 &&
+                       (heads > 0 || vec_ok<T>(D, {relation, input, output, outgrad, igrad, rgrad, scratch}));
+    if (fused) {
+        // one pass over the by-column order: input_grad by gather-reduce, relation_grad by REDG.F32x4 into zeros
+        CUDA_TRY(cudaMemsetAsync(rgrad, 0, (size_t)plan->R * (size_t)D * sizeof(T), stream));
+        rc = launch_pass<T, BWD_BOTH, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
+                                                (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads,
+                                                nullptr, (T *)rgrad);
+        if (rc) return rc;
+    } else {
+        rc = launch_pass<T, BWD_IN, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
                                               (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads);
-    if (rc) return rc;
-    rc = launch_pass<T, BWD_REL, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
-                                           (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream, heads);
-    if (rc) return rc;
+        if (rc) return rc;
+        rc = launch_pass<T, BWD_REL, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
+                                               (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream, heads);
+        if (rc) return rc;
+    }
     if (wgrad != nullptr && heads > 0) { set_error("weight_grad is not available in the head-major layout"); return 1; }
     if (wgrad != nullptr && plan->E > 0) {
         const SegOrder &so = plan->ord[FWD];
@@ -253,8 +269,9 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
     if (n == "update_impl") { set_update_impl(value); return 0; }
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
+    if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl)");
+    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl, bwd_fused_relgrad)");
     return 1;
 }
 

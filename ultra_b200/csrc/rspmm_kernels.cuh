@@ -36,6 +36,9 @@ namespace ultra {
 #ifndef ULTRA_FWD_UNROLL
 #define ULTRA_FWD_UNROLL 4  // edges per lane in flight in the single-gather passes (register budget: 64/thread)
 #endif
+#ifndef ULTRA_BOTH_UNROLL
+#define ULTRA_BOTH_UNROLL 4  // same for the fused backward pass (BWD_BOTH)
+#endif
 constexpr int kLanesPerEdge = 8;
 constexpr int kSubPerWarp = 32 / kLanesPerEdge;  // 4 items walked concurrently by one warp
 constexpr int kTileBytes = 128;
@@ -45,7 +48,13 @@ constexpr int kMergedBit = 1 << 30;  // items[k].z flag: member of a merged grou
 constexpr int kCtaThreads = 512;
 constexpr int kCtaWarps = kCtaThreads / 32;
 
-enum { FWD = 0, BWD_IN = 1, BWD_REL = 2 };
+enum { FWD = 0, BWD_IN = 1, BWD_REL = 2, BWD_BOTH = 3 };
+// BWD_BOTH (opt-in, tunable "bwd_fused_relgrad"): the BWD_IN pass that ALSO scatters each edge's relation_grad
+// contribution with one 16-byte vector reduction per lane (red.global.add.v4.f32 -> REDG.E.ADD.F32x4) into a pre-zeroed
+// relation_grad, so the two-gather BWD_REL pass disappears.  input_grad stays a deterministic gather-reduce;
+// relation_grad becomes order-dependent in the last bits, like the reference's atomicAdd backward (rspmm.cu:198-209).
+__host__ __device__ constexpr bool by_col(int mode) { return mode == BWD_IN || mode == BWD_BOTH; }
+__host__ __device__ constexpr int order_of(int mode) { return mode == BWD_BOTH ? BWD_IN : mode; }
 enum { S_ADD = 0, S_MIN = 1, S_MAX = 2, S_PNA = 3 };  // S_PNA: forward only, 4 aggregates in one pass (sum, sum of
                                                        // squares, max, min - the four rspmm calls of layers.py:211-215)
 enum { M_MUL = 0, M_ADD = 1 };
@@ -71,6 +80,15 @@ template <typename T> __device__ __forceinline__ void st_stream(T *p, const Vec<
         __stcs(reinterpret_cast<float4 *>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
     } else {
         __stcs(reinterpret_cast<double2 *>(p), make_double2(x.v[0], x.v[1]));
+    }
+}
+template <typename T> __device__ __forceinline__ void red_add_vec(T *p, const Vec<T> &x) {  // fire-and-forget += at L2
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3])
+                     : "memory");
+    } else {
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(x.v[0]) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(x.v[1]) : "memory");
     }
 }
 template <typename T> __device__ __forceinline__ void st_plain(T *p, const Vec<T> &x) {
@@ -138,6 +156,7 @@ template <typename T> struct SegParams {
     const T *output;    // (N, D)   backward only
     const T *outgrad;   // (N, D)   backward only
     T *dst;             // output / input_grad / relation_grad
+    T *rgrad;           // BWD_BOTH only: relation_grad (pre-zeroed), receives vector reductions
     T *partial;         // (num_slots, D), always flat
     long long dst_plane;      // S_PNA: element stride between the 4 output matrices (sum, sq_sum, max, min)
     long long partial_plane;  // S_PNA: element stride between the 4 partial buffers
@@ -157,12 +176,13 @@ template <typename T> struct SegParams {
 template <int MODE, int SUM, int MUL> struct Needs {
     static constexpr bool out = (MODE != FWD) && (SUM != S_ADD);                       // output[a] for dout/dy
     static constexpr bool inb = (MODE == BWD_REL) && (MUL == M_MUL || SUM != S_ADD);   // input[b]
-    static constexpr bool rel = (MODE == FWD) || (MODE == BWD_IN && (MUL == M_MUL || SUM != S_ADD));
-    static constexpr bool self = (MODE != FWD) && (SUM != S_ADD);   // the segment's own input / relation row
+    static constexpr bool rel = (MODE == FWD) || (by_col(MODE) && (MUL == M_MUL || SUM != S_ADD));
+    // the segment's own input / relation row (BWD_BOTH x mul: d x / d rel = input[col], the segment's row)
+    static constexpr bool self = ((MODE != FWD) && (SUM != S_ADD)) || (MODE == BWD_BOTH && MUL == M_MUL);
     static constexpr int red = (MODE == FWD) ? SUM : S_ADD;   // S_PNA: see acc_op()
     static constexpr int nacc = acc_count(red);
     static constexpr int gathers = 1 + (out ? 1 : 0) + (inb ? 1 : 0);  // row slices fetched per edge
-    static constexpr int unroll = (SUM != S_PNA && gathers == 1) ? ULTRA_FWD_UNROLL : ((SUM != S_PNA && gathers == 2 && SUM == S_ADD) ? 4 : 2);  // 64 regs
+    static constexpr int unroll = (MODE == BWD_BOTH) ? (gathers == 1 ? ULTRA_BOTH_UNROLL : 2) : (SUM != S_PNA && gathers == 1) ? ULTRA_FWD_UNROLL : ((SUM != S_PNA && gathers == 2 && SUM == S_ADD) ? 4 : 2);  // 64 regs
 };
 
 // shared-memory vector load through a 32-bit shared-window address (address math stays in 32 bits)
@@ -221,8 +241,9 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const char *out_c = reinterpret_cast<const char *>(p.output) + off_n;
     const char *in_c = reinterpret_cast<const char *>(p.input) + off_n;
     const char *rel_c = reinterpret_cast<const char *>(p.relation) + off_r;
-    const char *self_c = (MODE == BWD_IN) ? in_c : rel_c;
+    const char *self_c = by_col(MODE) ? in_c : rel_c;
     char *dst_c = reinterpret_cast<char *>(p.dst) + (MODE == BWD_REL ? off_r : off_n);
+    char *rg_c = reinterpret_cast<char *>(p.rgrad) + off_r;
     const char *bnd_c = reinterpret_cast<const char *>(p.boundary) + off_n;
     const bool has_bnd = (MODE == FWD) && p.boundary != nullptr;
     uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;
@@ -288,7 +309,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             // of holding U of them in registers - the registers are better spent on row gathers in flight.
             // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
             if (N::rel && REL_SMEM) rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
-            Vec<T> nxt[NA];
+            Vec<T> nxt[NA], rg;
 #pragma unroll
             for (int k = 0; k < V; k++) {
                 if (MODE == FWD) {
@@ -306,7 +327,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                     } else {
                         nxt[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], y);
                     }
-                } else if (MODE == BWD_IN) {
+                } else if (by_col(MODE)) {
                     // rspmm.cu:198-209  input_grad[col] += og * dout_dy * w * dx_din ; segment = col
                     T g = g1[u].v[k];
                     if (N::out) {
@@ -315,6 +336,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                         g = g * nary_bwd<SUM>(g2[u].v[k], y);
                     }
                     if (!UNITW) g = g * wv[u];
+                    if (MODE == BWD_BOTH) rg.v[k] = MUL == M_MUL ? g * self.v[k] : g;  // ... * dx_drel
                     if (MUL == M_MUL) g = g * rr[u].v[k];
                     nxt[0].v[k] = acc[0].v[k] + g;
                 } else {
@@ -334,6 +356,10 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             for (int a = 0; a < NA; a++)
 #pragma unroll
                 for (int k = 0; k < V; k++) acc[a].v[k] = ok[u] ? nxt[a].v[k] : acc[a].v[k];
+            if (MODE == BWD_BOTH) {  // relation_grad[type] += ... (rspmm.cu:207-208), 16 bytes per lane
+                if (ok[u] && st_ok)
+                    red_add_vec(reinterpret_cast<T *>(rg_c + (unsigned long long)((unsigned)m[u].y & 0x7fffffffu) * row_bytes), rg);
+            }
         };
         // one row-end test for the whole group of U edges (row ends are rare: the common path is pure FMA)
         int any = 0;
