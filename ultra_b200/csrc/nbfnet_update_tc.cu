@@ -20,6 +20,10 @@
 
 #include "../../include/ultra_rspmm.h"
 
+#ifndef ULTRA_POLL_NS
+#define ULTRA_POLL_NS 64  // sleep between failed mbarrier polls
+#endif
+
 namespace ultra {
 void set_error(const std::string &msg);
 
@@ -168,10 +172,15 @@ update_tc_kernel(const float *__restrict__ x, const float *__restrict__ u, const
         prefetch(tile + gridDim.x);  // global loads of the next tile overlap the MMAs and the epilogue
         // ---- epilogue part 1: all 16 warps.  Warp w reads TMEM lanes 32*(w&3).. (rows) x columns 16*(w>>2).. -------
         {
+            // back-off between polls: failed try_waits are wavefronts on the L1/shared data pipe that also feeds the
+            // tensor core's operand reads (ncu: 6 650 poll wavefronts per tile vs 2 304 operand wavefronts)
             unsigned done = 0;
-            while (!done)
+            while (true) {
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                              : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+                if (done) break;
+                __nanosleep(ULTRA_POLL_NS);
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int qd = warp & 3, grp = warp >> 2, r = qd * 32 + lane, cb = grp * 16;
             float v[16];
