@@ -147,7 +147,7 @@ def test_rspmm_heads_equals_flat_path(cuda_device, sum, mul, dtype, d, with_boun
         assert torch.equal(b1.grad, b2.grad)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05_3xtf32", "ffma", "tcgen05_pipelined"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05_pipelined", "ffma", "tcgen05_serial"])
 @pytest.mark.parametrize("layer_norm,relu,shortcut", [(True, True, True), (True, True, False), (False, True, True),
                                                       (True, False, False)])
 def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):

@@ -1,5 +1,5 @@
 """Fused layer epilogue (ultra_nbfnet_update_f32) at C2 size: every implementation timed with CUDA events and checked
-against an fp64 PyTorch evaluation.  impl: 0 = tcgen05 serial phases, 1 = FFMA, 2 = tcgen05 pipelined."""
+against an fp64 PyTorch evaluation.  impl: 0 = tcgen05 pipelined (default), 1 = FFMA, 2 = tcgen05 serial phases."""
 import json
 import os
 import sys

@@ -29,8 +29,8 @@ int launch_update_tc(const float *x, const float *u, const float *weight_t, cons
 int launch_update_tc2(const float *x, const float *u, const float *weight_t, const float *bias, const float *gamma,
                       const float *beta, float *out, int64_t num_rows, float eps, int layer_norm, int relu, int shortcut,
                       int sms, cudaStream_t stream);
-// 0 = tensor cores, serial tile phases (nbfnet_update_tc.cu); 1 = fp32 FFMA kernel of this file;
-// 2 = tensor cores, pipelined (nbfnet_update_tc2.cu)
+// 0 = tensor cores, pipelined (nbfnet_update_tc2.cu, default); 1 = fp32 FFMA kernel of this file;
+// 2 = tensor cores, serial tile phases (nbfnet_update_tc.cu, the first tcgen05 version)
 static std::atomic<int> g_update_impl{0};
 void set_update_impl(int v) { g_update_impl.store(v); }
 
@@ -176,10 +176,10 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
     const int sm_limit = ultra_rspmm_get_sm_limit();
     if (sm_limit > 0 && sm_limit < sms) sms = sm_limit;
     const int impl = g_update_impl.load();
-    if (impl == 2)
+    if (impl == 0)
         return launch_update_tc2(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,
                                  sms, stream);
-    if (impl == 0)
+    if (impl == 2)
         return launch_update_tc(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,
                                 sms, stream);
     const long long tiles = (num_rows + kBM - 1) / kBM;

@@ -8,7 +8,7 @@
 //   * the [x | u] operand tile is a ring of 4 K-chunks (32 fp32 columns each, hi + lo = 32 KB per chunk); as soon as a
 //     chunk is split and stored, one thread issues its 12 MMAs and commits them to that chunk's "empty" mbarrier, so the
 //     NEXT tile's chunk can be written while the tensor core is still working on the later chunks of this tile;
-//   * two TMEM accumulators (2 x 64 columns): the tensor core fills one while all 16 warps run the epilogue
+//   * two TMEM accumulators (2 x 128 columns): the tensor core fills one while all 16 warps run the epilogue
 //     (tcgen05.ld, bias, LayerNorm, ReLU, residual, store) of the previous tile out of the other;
 //   * the epilogue stores its 64-byte row pieces straight to global memory (full 32-byte sectors; L2 merges the four
 //     column groups of a row) and re-reads the residual x from L2 (it was fetched one tile earlier), so no shared-memory
@@ -66,8 +66,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return d;
 }
 
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kOut >> 3) << 17) | ((kBM >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+// An M = 128 MMA occupies the tensor pipe for 128 cycles whatever N <= 256 is (ncu: hmma_cycles_active = 128 x #MMA in
+// every version of this kernel), so the two products that share the A operand, Ah.Wh and Ah.Wl, are issued as ONE
+// N = 128 MMA against the stacked B operand [Wh ; Wl] (w_lo follows w_hi in shared memory = 8 more 8-row blocks); the
+// accumulator is 128 columns (Ah.Wh + Al.Wh | Ah.Wl) and the epilogue adds the halves.  32 MMAs per tile instead of 48.
+constexpr uint32_t idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((kBM >> 4) << 24); }
+constexpr int kAccCols = 2 * kOut;                  // TMEM columns per accumulator
 
 __device__ __forceinline__ void split_tf32(float a, float &hi, float &lo) {
     hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
@@ -131,7 +136,7 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
     }
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // W tiles: generic-proxy writes -> tensor-core reads
@@ -183,7 +188,11 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
                     float4 h, l;
                     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z);
                     split_tf32(v.w, h.w, l.w);
+#ifdef ULTRA_TF32_RAW_HI  // experiment: does kind::tf32 ignore the 13 low mantissa bits (hi == raw operand)?
+                    *reinterpret_cast<float4 *>(a_hi + off) = v;
+#else
                     *reinterpret_cast<float4 *>(a_hi + off) = h;
+#endif
                     *reinterpret_cast<float4 *>(a_lo + off) = l;
                 }
                 fetch_chunk(tile + step, c, i + 1 < n_my);  // next tile's rows of this chunk: in flight for a whole tile
@@ -192,19 +201,22 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
                 __syncthreads();
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(i & 1) * kOut;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(i & 1) * kAccCols;
+                    const uint64_t dah0 = dah + (uint64_t)(slot * (kAStageBytes >> 4));
+                    const uint64_t dal0 = dal + (uint64_t)(slot * (kAStageBytes >> 4));
+                    const uint64_t db0 = dwh + (uint64_t)(c * (kStageK / 8) * 16);
 #pragma unroll
-                    for (int prod = 0; prod < 3; prod++) {
-                        const uint64_t da0 = (prod == 2 ? dal : dah) + (uint64_t)(slot * (kAStageBytes >> 4));
-                        const uint64_t db0 = (prod == 1 ? dwl : dwh) + (uint64_t)(c * (kStageK / 8) * 16);
-#pragma unroll
-                        for (int ks = 0; ks < kStageK / 8; ks++) {  // one MMA = 8 tf32 of K = 2 chunks = 256 B
-                            const uint32_t acc = (c | prod | ks) ? 1u : 0u;
-                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                                         ::"r"(d_tmem), "l"(da0 + (uint64_t)(ks * (2 * kALbo >> 4))), "l"(db0 + (uint64_t)(ks * 16)),
-                                           "r"(kIdesc), "r"(acc) : "memory");
-                        }
+                    for (int ks = 0; ks < kStageK / 8; ks++) {  // one MMA = 8 tf32 of K = 2 chunks
+                        const uint64_t ka = (uint64_t)(ks * (2 * kALbo >> 4)), kb = (uint64_t)(ks * 16);
+                        const uint32_t acc = (c | ks) ? 1u : 0u;
+                        // Ah . [Wh ; Wl]^T -> columns 0..127
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                                     ::"r"(d_tmem), "l"(dah0 + ka), "l"(db0 + kb), "r"(idesc(2 * kOut)), "r"(acc) : "memory");
+                        // Al . Wh^T -> += columns 0..63
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                                     ::"r"(d_tmem), "l"(dal0 + ka), "l"(db0 + kb), "r"(idesc(kOut)), "r"(1u) : "memory");
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                                  ::"r"(bar0 + 8u * slot) : "memory");
@@ -219,19 +231,37 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
             const int e = i - 1;
             const long long m0 = (tile - step) * kBM;
             const int qd = warp & 3, grp = warp >> 2, r = qd * 32 + lane, cb = grp * 16;
+            // residual rows for part B (this SM fetched them a tile ago: L2 hits), issued before anything can stall
+            constexpr int kIt = kBM * 16 / kThreads;  // float4 per thread in part B: 4
+            float4 xr[kIt];
+#pragma unroll
+            for (int t = 0; t < kIt; t++) {
+                const int idx = tid + t * kThreads, rr = idx >> 4, c4 = idx & 15;
+                xr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (shortcut && m0 + rr < M) xr[t] = __ldg(reinterpret_cast<const float4 *>(x + (m0 + rr) * kOut) + c4);
+            }
             // part A: thread = (row r, 16 columns): accumulator -> bias -> LayerNorm -> ReLU -> staging (XOR-swizzled)
             mbar_wait(bar0 + 8u * (kSlots + (e & 1)), (unsigned)(e >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float v[16];
-            uint32_t *vr = reinterpret_cast<uint32_t *>(v);
+            float v[16], v2[16];
+            uint32_t *vr = reinterpret_cast<uint32_t *>(v), *vr2 = reinterpret_cast<uint32_t *>(v2);
+            const uint32_t t_acc = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((e & 1) * kAccCols + cb);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(vr[0]), "=r"(vr[1]), "=r"(vr[2]), "=r"(vr[3]), "=r"(vr[4]), "=r"(vr[5]), "=r"(vr[6]),
                            "=r"(vr[7]), "=r"(vr[8]), "=r"(vr[9]), "=r"(vr[10]), "=r"(vr[11]), "=r"(vr[12]), "=r"(vr[13]),
                            "=r"(vr[14]), "=r"(vr[15])
-                         : "r"(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((e & 1) * kOut + cb)));
+                         : "r"(t_acc));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(vr2[0]), "=r"(vr2[1]), "=r"(vr2[2]), "=r"(vr2[3]), "=r"(vr2[4]), "=r"(vr2[5]), "=r"(vr2[6]),
+                           "=r"(vr2[7]), "=r"(vr2[8]), "=r"(vr2[9]), "=r"(vr2[10]), "=r"(vr2[11]), "=r"(vr2[12]), "=r"(vr2[13]),
+                           "=r"(vr2[14]), "=r"(vr2[15])
+                         : "r"(t_acc + (uint32_t)kOut));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // ordered before the next barrier
+#pragma unroll
+            for (int c = 0; c < 16; c++) v[c] += v2[c];  // (Ah.Wh + Al.Wh) + Ah.Wl
             const float4 *prm4 = reinterpret_cast<const float4 *>(prm);
             float s = 0.f;
 #pragma unroll
@@ -268,14 +298,6 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
             __syncthreads();
             // part B: 16 lanes = one 256-byte row: residual add + store, every access a full 128-byte line per 8 lanes
             {
-                constexpr int kIt = kBM * 16 / kThreads;  // float4 per thread: 4
-                float4 xr[kIt];
-#pragma unroll
-                for (int t = 0; t < kIt; t++) {
-                    const int idx = tid + t * kThreads, rr = idx >> 4, c4 = idx & 15;
-                    xr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (shortcut && m0 + rr < M) xr[t] = __ldg(reinterpret_cast<const float4 *>(x + (m0 + rr) * kOut) + c4);
-                }
 #pragma unroll
                 for (int t = 0; t < kIt; t++) {
                     const int idx = tid + t * kThreads, rr = idx >> 4, c4 = idx & 15;
@@ -288,7 +310,7 @@ update_tc2_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
 }
 
 }  // namespace tc2
