@@ -29,8 +29,12 @@ int launch_update_tc(const float *x, const float *u, const float *weight_t, cons
 int launch_update_tc2(const float *x, const float *u, const float *weight_t, const float *bias, const float *gamma,
                       const float *beta, float *out, int64_t num_rows, float eps, int layer_norm, int relu, int shortcut,
                       int sms, cudaStream_t stream);
-// 0 = tensor cores, pipelined (nbfnet_update_tc2.cu, default); 1 = fp32 FFMA kernel of this file;
-// 2 = tensor cores, serial tile phases (nbfnet_update_tc.cu, the first tcgen05 version)
+int launch_update_tc3(const float *x, const float *u, const float *weight_t, const float *bias, const float *gamma,
+                      const float *beta, float *out, int64_t num_rows, float eps, int layer_norm, int relu, int shortcut,
+                      int sms, cudaStream_t stream);
+// 0 = tensor cores, pipelined 3xTF32 (nbfnet_update_tc2.cu, default); 1 = fp32 FFMA kernel of this file;
+// 2 = tensor cores, serial tile phases (nbfnet_update_tc.cu, the first tcgen05 version);
+// 3 = tensor cores, pipelined BF16x3 (nbfnet_update_tc3.cu)
 static std::atomic<int> g_update_impl{0};
 void set_update_impl(int v) { g_update_impl.store(v); }
 
@@ -178,6 +182,9 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
     const int impl = g_update_impl.load();
     if (impl == 0)
         return launch_update_tc2(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,
+                                 sms, stream);
+    if (impl == 3)
+        return launch_update_tc3(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,
                                  sms, stream);
     if (impl == 2)
         return launch_update_tc(x, u, weight_t, bias, ln_gamma, ln_beta, out, num_rows, ln_eps, layer_norm, relu, shortcut,

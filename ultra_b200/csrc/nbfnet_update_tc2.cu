@@ -67,10 +67,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
-// An M = 128 MMA occupies the tensor pipe for 128 cycles whatever N <= 256 is (ncu: hmma_cycles_active = 128 x #MMA in
-// every version of this kernel), so the two products that share the A operand, Ah.Wh and Ah.Wl, are issued as ONE
-// N = 128 MMA against the stacked B operand [Wh ; Wl] (w_lo follows w_hi in shared memory = 8 more 8-row blocks); the
-// accumulator is 128 columns (Ah.Wh + Al.Wh | Ah.Wl) and the epilogue adds the halves.  32 MMAs per tile instead of 48.
+// The two products that share the A operand, Ah.Wh and Ah.Wl, are issued as ONE N = 128 MMA against the stacked B
+// operand [Wh ; Wl] (w_lo follows w_hi in shared memory = 8 more 8-row blocks): the accumulator is 128 columns
+// (Ah.Wh + Al.Wh | Ah.Wl), the epilogue adds the halves.  32 MMAs per tile instead of 48; the tensor-active cycles do
+// not change (ncu: hmma_cycles_active is proportional to N) but Ah is fetched from shared memory once instead of twice.
 constexpr uint32_t idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((kBM >> 4) << 24); }
 constexpr int kAccCols = 2 * kOut;                  // TMEM columns per accumulator
 
