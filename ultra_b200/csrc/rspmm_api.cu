@@ -267,7 +267,11 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (name == nullptr) { set_error("set_tunable: null name"); return 1; }
     const std::string n(name);
     if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
-    if (n == "update_impl") { set_update_impl(value); return 0; }
+    if (n == "update_impl") {
+        if (value < 0 || value > 3) { set_error("set_tunable: update_impl must be 0 (tcgen05 pipelined), 1 (FFMA), 2 (tcgen05 serial) or 3 (tcgen05 BF16x3)"); return 1; }
+        set_update_impl(value);
+        return 0;
+    }
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }

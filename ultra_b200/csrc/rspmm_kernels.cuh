@@ -36,6 +36,9 @@ namespace ultra {
 #ifndef ULTRA_FWD_UNROLL
 #define ULTRA_FWD_UNROLL 4  // edges per lane in flight in the single-gather passes (register budget: 64/thread)
 #endif
+#ifndef ULTRA_META_PAIR
+#define ULTRA_META_PAIR 0  // 1: item metadata read two edges at a time (LDS.128) - to be measured
+#endif
 #ifndef ULTRA_BOTH_UNROLL
 #define ULTRA_BOTH_UNROLL 4  // same for the fused backward pass (BWD_BOTH)
 #endif
@@ -282,12 +285,25 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
         int2 m[U];
         T wv[U];
         bool ok[U];
+#if ULTRA_META_PAIR
+        // two edges' metadata per LDS.128: i and U are even (16-byte aligned), and entries past the item's end replicate
+        // its last edge, so no clamping is needed.  Each LDS is one wavefront on the L1/shared data pipe, the pipe this
+        // kernel saturates (gather + relation-row LDS + metadata = ~2.25 wavefronts per edge-tile + L1 fills)
+        static_assert(U % 2 == 0, "pair loads need an even unroll");
+#pragma unroll
+        for (int u = 0; u < U; u += 2)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(m[u].x), "=r"(m[u].y), "=r"(m[u + 1].x), "=r"(m[u + 1].y)
+                         : "r"(my_meta + (uint32_t)(i + u) * 8u));
+#endif
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int k = i + u;
             ok[u] = true;
             if (PRED) { ok[u] = k < len; k = k < len ? k : len_m1; }
+#if !ULTRA_META_PAIR
             asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(m[u].x), "=r"(m[u].y) : "r"(my_meta + (uint32_t)k * 8u));
+#endif
             wv[u] = T(1);
             if (!UNITW) wv[u] = __ldg(wp + k);
         }
