@@ -34,8 +34,7 @@ constexpr int kChunksK = kK / 4;                   // 16-byte chunks along K (4 
 constexpr int kSboBytes = kChunksK * 128;          // core-matrix row-block stride: 4096 B
 constexpr int kATileBytes = kBM * kK * 4;          // 64 KB
 constexpr int kWTileBytes = kOut * kK * 4;         // 32 KB
-constexpr int kLoads = kBM * kChunksK / kThreads;   // 16-byte loads per thread per tile: 16
-constexpr int kStageBytes = kBM * kOut * 4;        // 32 KB: LayerNorm output staged row-major, 16-byte chunks XOR-swizzled
+constexpr int kLoads = kBM * kChunksK / kThreads;   // 16-byte loads per thread per tile: 8
 constexpr size_t kSmemBytes = 2 * kATileBytes + 2 * kWTileBytes + 1024 + 3 * 64 * 4 + 2 * 4 * kBM * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,7 +113,7 @@ update_tc_kernel(const float *__restrict__ x, const float *__restrict__ u, const
 
     const long long num_tiles = (M + kBM - 1) / kBM;
     // software pipeline: the NEXT tile's [x | u] rows are fetched into registers while the tensor core and the
-    // epilogue work on the current tile (16 independent 16-byte loads per thread = 64 KB in flight per SM)
+    // epilogue work on the current tile (8 independent 16-byte loads per thread = 64 KB in flight per SM)
     float4 pre[kLoads];
     auto prefetch = [&](long long t_) {
         const long long mm = t_ * kBM;

@@ -46,7 +46,14 @@ constexpr int kLanesPerEdge = 8;
 constexpr int kSubPerWarp = 32 / kLanesPerEdge;  // 4 items walked concurrently by one warp
 constexpr int kTileBytes = 128;
 constexpr int kItemEdges = 64;   // max edges of a whole-segment item and chunk length of a long segment
-constexpr int kMetaStageBytes = 4 * 64 * 8;  // per warp: the (a, b) metadata of its 4 items, staged in shared memory
+#ifndef ULTRA_META_PAD
+#define ULTRA_META_PAD 0  // bytes of padding between the 4 sub-groups' metadata regions (16: bank-conflict-free) - to be measured
+#endif
+// per warp: the (a, b) metadata of its 4 items, staged in shared memory.  The 4 sub-groups read their entry k in the same
+// instruction; with 512-byte regions those 4 addresses fall on the same banks (ncu: 52 M conflict wavefronts per forward
+// call, 12 % of the data-pipe traffic), with 528-byte regions they are 16 bytes apart.
+constexpr int kMetaSubBytes = kItemEdges * 8 + ULTRA_META_PAD;
+constexpr int kMetaStageBytes = kSubPerWarp * kMetaSubBytes;
 constexpr int kMergedBit = 1 << 30;  // items[k].z flag: member of a merged group of 4 full chunks
 constexpr int kCtaThreads = 512;
 constexpr int kCtaWarps = kCtaThreads / 32;
@@ -270,7 +277,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     // with a ~30-cycle broadcast LDS instead of a dependent global load, so each group of U edges exposes ONE long
     // latency (the row gather) instead of two (metadata -> gather).  The stall profile was 72 % long_scoreboard.
     // Entries past the item's end replicate its last edge, so the predicated tail needs no index clamping.
-    const uint32_t my_meta = meta_s_addr + (uint32_t)sg * (kItemEdges * 8);
+    const uint32_t my_meta = meta_s_addr + (uint32_t)sg * kMetaSubBytes;
     __syncwarp();  // the previous item's metadata is no longer being read by the other lanes
 #pragma unroll
     for (int t = 0; t < kItemEdges / kLanesPerEdge; t++) {
