@@ -147,7 +147,7 @@ def test_rspmm_heads_equals_flat_path(cuda_device, sum, mul, dtype, d, with_boun
         assert torch.equal(b1.grad, b2.grad)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05_pipelined", "ffma", "tcgen05_serial"])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_pipelined", "ffma", "tcgen05_serial", "tcgen05_bf16x3"])
 @pytest.mark.parametrize("layer_norm,relu,shortcut", [(True, True, True), (True, True, False), (False, True, True),
                                                       (True, False, False)])
 def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
@@ -175,7 +175,7 @@ def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
             if shortcut:
                 ref = ref + x.double()
         torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=2e-5)
-    _capi.set_tunable("update_impl", 0)
+    _capi.set_tunable("update_impl", -1)
 
 
 @pytest.mark.parametrize("message,aggregate", [("distmult", "sum"), ("transe", "max"), ("distmult", "mean")])

@@ -1,0 +1,57 @@
+#!/bin/bash
+# One bounded GPU session (run under gpurun): A/B the compile-time forward-kernel variants, validate the winner with the
+# GPU test-suite, validate + time the BF16x3 layer epilogue, and take a bench line with what won.  Every step has its
+# own timeout and writes into gpurun_out/ as it goes, so a cut-off session still leaves its earlier results.
+set +e
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+t0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" | tee -a gpurun_out/session.log; }
+
+stamp "ab_bench"
+timeout 220 python tools/ab_bench.py --out gpurun_out/ab.jsonl --timeout 90 > gpurun_out/ab.log 2>&1
+WIN=$(python - <<'EOF'
+import json
+try:
+    print([json.loads(l) for l in open("gpurun_out/ab.jsonl")][-1]["winner_lib"])
+except Exception:
+    print("")
+EOF
+)
+[ -n "$WIN" ] && [ -f "$WIN" ] || WIN="$PWD/ultra_b200/lib/libultra_rspmm.so"
+stamp "winner: $WIN"
+
+stamp "pytest -m gpu on the winner (BF16x3 epilogue cases run separately below)"
+ULTRA_RSPMM_LIB=$WIN timeout 200 python -m pytest tests -m gpu -x -q -k "not bf16x3" > gpurun_out/pytest_winner.log 2>&1
+stamp "pytest rc=$? : $(tail -1 gpurun_out/pytest_winner.log)"
+
+stamp "BF16x3 epilogue: unit cases"
+timeout 90 python -m pytest tests/test_layer_gpu.py -m gpu -q -k "bf16x3" > gpurun_out/pytest_bf16x3.log 2>&1
+RC3=$?
+stamp "bf16x3 rc=$RC3 : $(tail -1 gpurun_out/pytest_bf16x3.log)"
+stamp "BF16x3 epilogue: C2-size timing and error against fp64"
+timeout 90 python tools/update_bench.py 0,3 > gpurun_out/update_bf16x3.jsonl 2> gpurun_out/update_bf16x3.err
+stamp "update_bench rc=$? : $(tail -1 gpurun_out/update_bf16x3.jsonl)"
+IMPL=0
+if [ $RC3 -eq 0 ]; then
+    stamp "layer tests with the BF16x3 epilogue as the library default"
+    ULTRA_UPDATE_IMPL=3 ULTRA_RSPMM_LIB=$WIN timeout 120 python -m pytest tests/test_layer_gpu.py -m gpu -x -q > gpurun_out/pytest_layer_impl3.log 2>&1
+    RCL=$?
+    stamp "layer impl3 rc=$RCL : $(tail -1 gpurun_out/pytest_layer_impl3.log)"
+    # adopt it for the bench line only if it is also faster at C2 size
+    IMPL=$(python - <<'EOF'
+import json
+try:
+    r = {d["impl"]: d for d in (json.loads(l) for l in open("gpurun_out/update_bf16x3.jsonl") if l.startswith("{"))}
+    ok = r[3]["ms_med"] < 0.97 * r[0]["ms_med"] and r[3]["max_abs_err_vs_fp64"] < 2e-5
+    print(3 if ok else 0)
+except Exception:
+    print(0)
+EOF
+)
+    [ $RCL -eq 0 ] || IMPL=0
+fi
+stamp "bench.py with winner lib, update_impl=$IMPL"
+ULTRA_UPDATE_IMPL=$IMPL ULTRA_RSPMM_LIB=$WIN timeout 240 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+stamp "bench rc=$? : $(head -c 300 gpurun_out/bench_final.json)"
+stamp "done"

@@ -1,5 +1,5 @@
 """Fused layer epilogue (ultra_nbfnet_update_f32) at C2 size: every implementation timed with CUDA events and checked
-against an fp64 PyTorch evaluation.  impl: 0 = tcgen05 pipelined (default), 1 = FFMA, 2 = tcgen05 serial phases."""
+against an fp64 PyTorch evaluation.  impl: 0 = tcgen05 pipelined (default), 1 = FFMA, 2 = tcgen05 serial phases, 3 = tcgen05 pipelined BF16x3."""
 import json
 import os
 import sys
@@ -37,4 +37,4 @@ for impl in impls:
     gb = M * (128 + 64) * 4 / 1e9
     print(json.dumps({"impl": impl, "rows": M, "ms_med": round(med, 4), "ms_min": round(best, 4),
                       "max_abs_err_vs_fp64": err, "compulsory_GBs": round(gb / med * 1e3, 1)}), flush=True)
-_capi.set_tunable("update_impl", 0)
+_capi.set_tunable("update_impl", -1)

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/ultra_rspmm.h"
@@ -35,8 +36,15 @@ int launch_update_tc3(const float *x, const float *u, const float *weight_t, con
 // 0 = tensor cores, pipelined 3xTF32 (nbfnet_update_tc2.cu, default); 1 = fp32 FFMA kernel of this file;
 // 2 = tensor cores, serial tile phases (nbfnet_update_tc.cu, the first tcgen05 version);
 // 3 = tensor cores, pipelined BF16x3 (nbfnet_update_tc3.cu)
-static std::atomic<int> g_update_impl{0};
-void set_update_impl(int v) { g_update_impl.store(v); }
+// -1 (tunable only) = back to the library default, which the environment variable ULTRA_UPDATE_IMPL=0..3 can override at
+// load time (A/B runs of the whole test-suite against one implementation without touching the callers)
+constexpr int kDefaultUpdateImpl = 0;
+static int initial_update_impl() {
+    const char *e = std::getenv("ULTRA_UPDATE_IMPL");
+    return (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : kDefaultUpdateImpl;
+}
+static std::atomic<int> g_update_impl{initial_update_impl()};
+void set_update_impl(int v) { g_update_impl.store(v < 0 ? initial_update_impl() : v); }
 
 namespace {
 

@@ -268,7 +268,7 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     const std::string n(name);
     if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
     if (n == "update_impl") {
-        if (value < 0 || value > 3) { set_error("set_tunable: update_impl must be 0 (tcgen05 pipelined), 1 (FFMA), 2 (tcgen05 serial) or 3 (tcgen05 BF16x3)"); return 1; }
+        if (value < -1 || value > 3) { set_error("set_tunable: update_impl must be 0 (tcgen05 pipelined), 1 (FFMA), 2 (tcgen05 serial), 3 (tcgen05 BF16x3) or -1 (library default)"); return 1; }
         set_update_impl(value);
         return 0;
     }
