@@ -54,4 +54,16 @@ fi
 stamp "bench.py with winner lib, update_impl=$IMPL"
 ULTRA_UPDATE_IMPL=$IMPL ULTRA_RSPMM_LIB=$WIN timeout 240 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 stamp "bench rc=$? : $(head -c 300 gpurun_out/bench_final.json)"
+if [ "$WIN" != "$PWD/ultra_b200/lib/libultra_rspmm.so" ]; then
+    stamp "ncu --set full of the winner's forward kernel"
+    ULTRA_RSPMM_LIB=$WIN timeout 150 ncu --set full --clock-control none --import-source on -k regex:seg_reduce_kernel -s 3 -c 1 \
+        -f -o gpurun_out/r01_fwd_v6 python tools/kbench.py --alphas 1.0 > gpurun_out/ncu_fwd_v6.log 2>&1
+    stamp "ncu rc=$?"
+fi
+if [ "$IMPL" = "3" ]; then
+    stamp "ncu --set full of the BF16x3 epilogue"
+    timeout 120 ncu --set full --clock-control none --import-source on -k regex:update_tc3_kernel -s 2 -c 1 \
+        -f -o gpurun_out/r01_update_v9 python tools/update_bench.py 3 > gpurun_out/ncu_update_v9.log 2>&1
+    stamp "ncu rc=$?"
+fi
 stamp "done"
