@@ -90,3 +90,59 @@ def assert_close_with_truth(actual, expected32, truth64, what, rtol=1e-5):
         assert not bool(bad.any()), "%s vs %s: %d elements beyond budget, worst %.3e (budget there %.3e, ref err %.3e)" % (
             what, name, int(bad.sum()), float(err[bad].max()), float(budget[bad][err[bad].argmax()]),
             float(ref_err[bad][err[bad].argmax()]))
+
+
+# ---- layer-level fixture (tests/golden/layer_golden.npz, made by tests/golden/make_layer_golden.py) ------------------
+LAYER_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "layer_golden.npz")
+
+
+def load_layer_golden():
+    return np.load(LAYER_GOLDEN)
+
+
+def ultra_modules_from_state_dict(sd, device="cpu"):
+    """The product-side layer classes (ultra_b200.layer) populated from a reference checkpoint's state-dict:
+    (relation_layers, entity_layers), configuration of the shipped ultra_* checkpoints (distmult, sum, layer_norm,
+    relu; /root/reference/config/transductive/inference.yaml).  Keys are loaded with strict=True, i.e. the module
+    parameter names are the reference's."""
+    from ultra_b200.layer import GeneralizedRelationalConv
+
+    def stack(prefix, **kw):
+        n = 1 + max(int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix))
+        layers = []
+        for i in range(n):
+            layer = GeneralizedRelationalConv(64, 64, kw["num_relation"], 64, "distmult", "sum", layer_norm=True,
+                                              activation="relu", dependent=False,
+                                              project_relations=kw["project_relations"])
+            own = {k[len(prefix) + len(str(i)) + 1:]: v for k, v in sd.items() if k.startswith("%s%d." % (prefix, i))}
+            layer.load_state_dict(own, strict=True)
+            layers.append(layer.to(device).eval())
+        return layers
+
+    relation_layers = stack("relation_model.layers.", num_relation=4, project_relations=False)
+    entity_layers = stack("entity_model.layers.", num_relation=1, project_relations=True)
+    return relation_layers, entity_layers
+
+
+def ultra_forward(relation_layers, entity_layers, sd, fx, device="cpu"):
+    """Ultra.forward (/root/reference/ultra/models.py:18-27) through ultra_b200.layer: relation-graph stack ->
+    relation representations -> entity-graph stack -> tail scores.  Returns (rel_repr, h6, score)."""
+    from ultra_b200.layer import bellmanford_entity
+
+    t = lambda k: torch.from_numpy(np.asarray(fx[k])).to(device)  # noqa: E731
+    num_node, num_rel = int(fx["num_node"]), int(fx["num_relation"])
+    h_index, r_index, t_index = t("h_index"), t("r_index"), t("t_index")
+    # RelNBFNet.bellmanford (models.py:55-95): all-ones query at the query relation, output = last hidden
+    ones = torch.ones(len(r_index), 64, device=device)
+    rel_repr = bellmanford_entity(relation_layers, ones, r_index, t("rel_edge_index"), t("rel_edge_type"), num_rel)
+    # EntityNBFNet.forward / bellmanford (models.py:131-186)
+    for layer in entity_layers:
+        layer.relation = rel_repr
+    query = rel_repr[torch.arange(len(r_index), device=device), r_index]
+    h6 = bellmanford_entity(entity_layers, query, h_index, t("edge_index"), t("edge_type"), num_node)
+    feature = torch.cat([h6, query.unsqueeze(1).expand(-1, num_node, -1)], dim=-1)
+    f = feature.gather(1, t_index.unsqueeze(-1).expand(-1, -1, feature.shape[-1]))
+    w = lambda k: sd[k].to(device)  # noqa: E731
+    f = torch.relu(torch.nn.functional.linear(f, w("entity_model.mlp.0.weight"), w("entity_model.mlp.0.bias")))
+    score = torch.nn.functional.linear(f, w("entity_model.mlp.2.weight"), w("entity_model.mlp.2.bias")).squeeze(-1)
+    return rel_repr, h6, score

@@ -22,7 +22,7 @@ EOF
 stamp "winner: $WIN"
 
 stamp "pytest -m gpu on the winner (BF16x3 epilogue cases run separately below)"
-ULTRA_RSPMM_LIB=$WIN timeout 200 python -m pytest tests -m gpu -x -q -k "not bf16x3" > gpurun_out/pytest_winner.log 2>&1
+ULTRA_RSPMM_LIB=$WIN timeout 200 python -m pytest tests -m gpu -q --maxfail=5 -k "not bf16x3" > gpurun_out/pytest_winner.log 2>&1
 stamp "pytest rc=$? : $(tail -1 gpurun_out/pytest_winner.log)"
 
 stamp "BF16x3 epilogue: unit cases"
