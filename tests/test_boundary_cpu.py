@@ -118,3 +118,18 @@ def test_tunables_are_host_only_and_validated(capi):
         _capi.set_tunable("update_impl", 9)
     with pytest.raises(RuntimeError, match="update_impl must be"):
         _capi.set_tunable("update_impl", -2)
+
+
+def test_plain_c_consumer(capi, tmp_path):
+    """The boundary is a C ABI: a C99 program compiled against include/ultra_rspmm.h with -pedantic links to the library
+    and calls its host-side entry points (what a cgo / JNI / N-API binding on the reference side would do)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "ultra_b200", "lib")
+    exe = str(tmp_path / "abi_consumer")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "abi", "abi_consumer.c"), "-o", exe, "-L", lib_dir, "-lultra_rspmm",
+                    "-Wl,-rpath," + lib_dir], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert r.stdout.startswith("ultra_rspmm sm_100a")
