@@ -38,7 +38,7 @@ int launch_update_tc3(const float *x, const float *u, const float *weight_t, con
 // 3 = tensor cores, pipelined BF16x3 (nbfnet_update_tc3.cu)
 // -1 (tunable only) = back to the library default, which the environment variable ULTRA_UPDATE_IMPL=0..3 can override at
 // load time (A/B runs of the whole test-suite against one implementation without touching the callers)
-constexpr int kDefaultUpdateImpl = 0;
+constexpr int kDefaultUpdateImpl = 3;
 static int initial_update_impl() {
     const char *e = std::getenv("ULTRA_UPDATE_IMPL");
     return (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : kDefaultUpdateImpl;

@@ -37,7 +37,7 @@ namespace ultra {
 #define ULTRA_FWD_UNROLL 4  // edges per lane in flight in the single-gather passes (register budget: 64/thread)
 #endif
 #ifndef ULTRA_META_PAIR
-#define ULTRA_META_PAIR 0  // 1: item metadata read two edges at a time (LDS.128) - to be measured
+#define ULTRA_META_PAIR 1  // item metadata read two edges at a time (explicit LDS.128); 0 = one LDS.64 per edge
 #endif
 #ifndef ULTRA_BOTH_UNROLL
 #define ULTRA_BOTH_UNROLL 4  // same for the fused backward pass (BWD_BOTH)
@@ -47,7 +47,7 @@ constexpr int kSubPerWarp = 32 / kLanesPerEdge;  // 4 items walked concurrently 
 constexpr int kTileBytes = 128;
 constexpr int kItemEdges = 64;   // max edges of a whole-segment item and chunk length of a long segment
 #ifndef ULTRA_META_PAD
-#define ULTRA_META_PAD 0  // bytes of padding between the 4 sub-groups' metadata regions (16: bank-conflict-free) - to be measured
+#define ULTRA_META_PAD 16  // bytes of padding between the 4 sub-groups' metadata regions (16: bank-conflict-free; 0: none)
 #endif
 // per warp: the (a, b) metadata of its 4 items, staged in shared memory.  The 4 sub-groups read their entry k in the same
 // instruction; with 512-byte regions those 4 addresses fall on the same banks (ncu: 52 M conflict wavefronts per forward
