@@ -45,10 +45,11 @@ const char *ultra_rspmm_version(void);
  * Process-wide launch tunables.  "sm_limit": size the persistent grids for this many SMs (0 = all) so that a
  * concurrent NCCL collective (the overlapped all-gather of node states, ultra_b200/shard.py) finds free SMs.
  * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
- * "update_impl": 0 (default) runs ultra_nbfnet_update_f32 on the tensor cores (tcgen05, 3xTF32 split, fp32-level
- * accuracy; pipelined kernel nbfnet_update_tc2.cu), 1 selects the plain fp32 FFMA kernel, 2 the first, non-pipelined
- * tcgen05 kernel (nbfnet_update_tc.cu), 3 the pipelined kernel with a BF16x3 operand split on kind::f16
- * (nbfnet_update_tc3.cu), -1 restores the library default (which ULTRA_UPDATE_IMPL=0..3 in the environment overrides
+ * "update_impl" selects the kernel behind ultra_nbfnet_update_f32: 3 (library default) = tensor cores, pipelined tcgen05
+ * kernel with a BF16x3 operand split on kind::f16 (nbfnet_update_tc3.cu, fp32-level accuracy: 3.2e-6 max abs error
+ * against fp64 on outputs of magnitude 7); 0 = the same pipeline with a 3xTF32 split on kind::tf32
+ * (nbfnet_update_tc2.cu); 1 = plain fp32 FFMA kernel; 2 = the first, non-pipelined tcgen05 kernel
+ * (nbfnet_update_tc.cu); -1 restores the library default (which ULTRA_UPDATE_IMPL=0..3 in the environment overrides
  * at load time).  "host_copy_split": row blocks per slab copy in forward_host.
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a

@@ -5,9 +5,10 @@
 // five PyTorch kernels and ~8 passes over the (B, N, 64) state become one pass (read x, read u, write out).
 //
 // x, u, out are (M, 64) fp32 row-major with M = heads * nodes -- exactly the (B, N, 64) layer state, no transposes.
-// Arithmetic is plain fp32 FFMA (K = 128 accumulated in order): the reference's Linear is an fp32 GEMM and the
-// parity bar is 1e-5, so TF32 tensor-core MMA (10-bit mantissa) is not an option and 3xTF32 emulation would need
-// three tcgen05 passes for a GEMM that is memory-bound anyway (1.43 GB moved vs 30 GFLOP: 0.22 ms vs 0.42 ms).
+// This file holds the plain fp32 FFMA kernel (K = 128 accumulated in order; update_impl = 1): the reference's Linear is an
+// fp32 GEMM and the parity bar is 1e-5, so a single TF32 tensor-core MMA (10-bit mantissa) is not an option.  The
+// tensor-core kernels that became the default afterwards split the operands instead (3xTF32 / BF16x3, fp32 accumulation
+// in TMEM): nbfnet_update_tc.cu, _tc2.cu, _tc3.cu; the dispatcher at the bottom of this file selects among the four.
 //
 // CTA = 256 threads, 128 rows per tile, persistent over tiles.  smem: A tile [128][132] (x | u, padded) + Wt [128][64].
 // Thread (ty, tx) owns rows ty*8..+8, columns tx*4..+4: per 4 k-steps 8+4 LDS.128 feed 128 FFMA.
@@ -33,9 +34,9 @@ int launch_update_tc2(const float *x, const float *u, const float *weight_t, con
 int launch_update_tc3(const float *x, const float *u, const float *weight_t, const float *bias, const float *gamma,
                       const float *beta, float *out, int64_t num_rows, float eps, int layer_norm, int relu, int shortcut,
                       int sms, cudaStream_t stream);
-// 0 = tensor cores, pipelined 3xTF32 (nbfnet_update_tc2.cu, default); 1 = fp32 FFMA kernel of this file;
+// 0 = tensor cores, pipelined 3xTF32 (nbfnet_update_tc2.cu); 1 = fp32 FFMA kernel of this file;
 // 2 = tensor cores, serial tile phases (nbfnet_update_tc.cu, the first tcgen05 version);
-// 3 = tensor cores, pipelined BF16x3 (nbfnet_update_tc3.cu)
+// 3 = tensor cores, pipelined BF16x3 (nbfnet_update_tc3.cu) - the default: 0.386 vs 0.404 ms at C2 size, same error
 // -1 (tunable only) = back to the library default, which the environment variable ULTRA_UPDATE_IMPL=0..3 can override at
 // load time (A/B runs of the whole test-suite against one implementation without touching the callers)
 constexpr int kDefaultUpdateImpl = 3;
