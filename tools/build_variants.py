@@ -12,10 +12,15 @@ from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ultra_b200 import build as lib_build  # noqa: E402
 
+# Round-1 A/B (profiles/r01_ab_meta_variants.jsonl) made PAD=16 + PAIR=1 the default; "nopadpair" is the old build.
+# Queued for the next session (ptxas, 64-register cap: U=4 24 B of spills, U=6 104 B with one LDL per loop iteration,
+# U=8 312 B, of which the unit-weight path - the only one ULTRA uses - holds 116 B: 3 LDL + 1 STL per loop iteration
+# next to 8 LDG.128; the non-unit-weight path stays at 4): more row gathers in flight per lane - the forward kernel is latency-bound (long_scoreboard), so bytes in
+# flight are what count.  U=6 does not divide the 64 staged entries, so it needs the clamped single loads (PAIR=0).
 VARIANTS = {
-    "pad16": ["-DULTRA_META_PAD=16"],
-    "pair": ["-DULTRA_META_PAIR=1"],
-    "padpair": ["-DULTRA_META_PAD=16", "-DULTRA_META_PAIR=1"],
+    "nopadpair": ["-DULTRA_META_PAD=0", "-DULTRA_META_PAIR=0"],
+    "unroll6": ["-DULTRA_FWD_UNROLL=6", "-DULTRA_FWD_UNROLL_W=4", "-DULTRA_META_PAIR=0"],
+    "unroll8": ["-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"],
 }
 OUT_DIR = os.path.join(lib_build.LIB_DIR, "variants")
 

@@ -36,6 +36,9 @@ namespace ultra {
 #ifndef ULTRA_FWD_UNROLL
 #define ULTRA_FWD_UNROLL 4  // edges per lane in flight in the single-gather passes (register budget: 64/thread)
 #endif
+#ifndef ULTRA_FWD_UNROLL_W
+#define ULTRA_FWD_UNROLL_W ULTRA_FWD_UNROLL  // same, for the (rare) non-unit-weight path, which also holds U weights per lane
+#endif
 #ifndef ULTRA_META_PAIR
 #define ULTRA_META_PAIR 1  // item metadata read two edges at a time (explicit LDS.128); 0 = one LDS.64 per edge
 #endif
@@ -222,7 +225,8 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     using N = Needs<MODE, SUM, MUL>;
     constexpr int V = VecN<T>::value;
     constexpr int TILE = kLanesPerEdge * V;
-    constexpr int U = N::unroll;
+    constexpr bool kSingleGather = MODE != BWD_BOTH && SUM != S_PNA && N::gathers == 1;
+    constexpr int U = (kSingleGather && !UNITW) ? ULTRA_FWD_UNROLL_W : N::unroll;
     const int lane = threadIdx.x & 31;
     const int q = lane & (kLanesPerEdge - 1);
     const int sg = lane >> 3;
@@ -297,6 +301,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
         // its last edge, so no clamping is needed.  Each LDS is one wavefront on the L1/shared data pipe, the pipe this
         // kernel saturates (gather + relation-row LDS + metadata = ~2.25 wavefronts per edge-tile + L1 fills)
         static_assert(U % 2 == 0, "pair loads need an even unroll");
+        static_assert(kItemEdges % U == 0, "pair loads are not clamped: the last group must end inside the 64 staged entries");
 #pragma unroll
         for (int u = 0; u < U; u += 2)
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
