@@ -14,6 +14,8 @@ whole batch (the call GeneralizedRelationalConv.message_and_aggregate makes, /ro
               and D2H of the output inside the timed region (pipelined column slabs in the C ABI)
   roofline  : algorithmic bytes (edge-gather model) / measured per-call device time vs the measured
               HBM copy peak in MEASURED_PEAKS.json
+  backward  : (extra, SURVEY 8d iii) ms per ultra_rspmm_backward call on the same workload; plan_build_ms also carries
+              forward_incl_plan_build_ms (SURVEY 8d ii: the reference wrapper sorts on every call)
   cpu_baseline / --impl reference : the reference's own CPU kernel (oracle/_ref, built from /root/reference by
               oracle/build_ref.py) on this box's host cores
 
@@ -275,6 +277,33 @@ def main():
     e2e_value = world * E * e2e_steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     layer_info = None if args.no_layer else bench_layer(wl, device, world, rank)
+    # ---- rspmm backward (relation_grad + input_grad, deterministic two-pass default), untimed extras
+    # are reported beside the headline and can never fail the run
+    backward_info = None
+    try:
+        og_d = torch.randn_like(x_d)
+        ig_d, rg_d = torch.empty_like(x_d), torch.empty_like(rel_d)
+
+        def bwd():
+            rc = lib.ultra_rspmm_backward(plan.handle, 0, 0, 0, rel_d.data_ptr(), x_d.data_ptr(), out_d.data_ptr(),
+                                          og_d.data_ptr(), None, rg_d.data_ptr(), ig_d.data_ptr(), D,
+                                          scratch.data_ptr(), scratch.numel(), _stream_ptr(device))
+            if rc != 0:
+                raise RuntimeError(lib.ultra_rspmm_last_error().decode())
+        for _ in range(2):
+            bwd()
+        torch.cuda.synchronize()  # per-rank (no collective inside the guarded extras)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(5):
+            bwd()
+        b1.record()
+        torch.cuda.synchronize()  # per-rank (no collective inside the guarded extras)
+        backward_info = {"ms_per_call": b0.elapsed_time(b1) / 5, "calls": 5,
+                         "what": "ultra_rspmm_backward add-mul, same workload: input_grad + relation_grad, no atomics"}
+        del og_d, ig_d, rg_d
+    except Exception as exc:  # noqa: BLE001 - extras only
+        backward_info = {"error": repr(exc)}
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -299,7 +328,9 @@ def main():
                     "api": "ultra_b200.rspmm.generalized_rspmm(pinned CPU tensors) -> ultra_rspmm_forward_host",
                     "checksum": checksum},
             "gpu_launches": launches_per_step * args.steps,
+            "backward": backward_info,
             "plan_build_ms": {"warm": plan_build_ms, "first_call_incl_context": first_plan_ms,
+                              "forward_incl_plan_build_ms": kernel_ms + plan_build_ms,
                               "note": "once per graph, outside the timed region; the reference wrapper re-sorts the "
                                       "edges on every call (rspmm.py:174-178)"},
             "clocks": clocks,
