@@ -1,69 +1,41 @@
 #!/bin/bash
-# One bounded GPU session (run under gpurun): A/B the compile-time forward-kernel variants, validate the winner with the
-# GPU test-suite, validate + time the BF16x3 layer epilogue, and take a bench line with what won.  Every step has its
-# own timeout and writes into gpurun_out/ as it goes, so a cut-off session still leaves its earlier results.
+# One bounded GPU session (run under gpurun): A/B the compile-time forward-kernel variants that tools/build_variants.py
+# built (ultra_b200/lib/variants/), validate the winner with the full GPU test-suite, take a bench line and an ncu
+# capture with it.  Every step has its own timeout and writes into gpurun_out/ as it goes, so a cut-off session still
+# leaves its earlier results.  Round-1 use: profiles/r01_ab_session.log (metadata staging variants, BF16x3 epilogue).
+#   python tools/build_variants.py && gpurun --timeout 480 -- 'bash tools/gpu_ab_session.sh'
 set +e
-mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
 t0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" | tee -a gpurun_out/session.log; }
+DEFAULT_LIB="$PWD/ultra_b200/lib/libultra_rspmm.so"
 
 stamp "ab_bench"
-timeout 220 python tools/ab_bench.py --out gpurun_out/ab.jsonl --timeout 90 > gpurun_out/ab.log 2>&1
-WIN=$(python - <<'EOF'
+timeout 300 python tools/ab_bench.py --out gpurun_out/ab.jsonl --timeout 90 > gpurun_out/ab.log 2>&1
+WIN=$(python - <<'PY'
 import json
 try:
     print([json.loads(l) for l in open("gpurun_out/ab.jsonl")][-1]["winner_lib"])
 except Exception:
     print("")
-EOF
+PY
 )
-[ -n "$WIN" ] && [ -f "$WIN" ] || WIN="$PWD/ultra_b200/lib/libultra_rspmm.so"
+[ -n "$WIN" ] && [ -f "$WIN" ] || WIN="$DEFAULT_LIB"
 stamp "winner: $WIN"
 
-stamp "pytest -m gpu on the winner (BF16x3 epilogue cases run separately below)"
-ULTRA_RSPMM_LIB=$WIN timeout 200 python -m pytest tests -m gpu -q --maxfail=5 -k "not bf16x3" > gpurun_out/pytest_winner.log 2>&1
+stamp "pytest -m gpu on the winner"
+ULTRA_RSPMM_LIB=$WIN timeout 240 python -m pytest tests -m gpu -q --maxfail=5 > gpurun_out/pytest_winner.log 2>&1
 stamp "pytest rc=$? : $(tail -1 gpurun_out/pytest_winner.log)"
 
-stamp "BF16x3 epilogue: unit cases"
-timeout 90 python -m pytest tests/test_layer_gpu.py -m gpu -q -k "bf16x3" > gpurun_out/pytest_bf16x3.log 2>&1
-RC3=$?
-stamp "bf16x3 rc=$RC3 : $(tail -1 gpurun_out/pytest_bf16x3.log)"
-stamp "BF16x3 epilogue: C2-size timing and error against fp64"
-timeout 90 python tools/update_bench.py 0,3 > gpurun_out/update_bf16x3.jsonl 2> gpurun_out/update_bf16x3.err
-stamp "update_bench rc=$? : $(tail -1 gpurun_out/update_bf16x3.jsonl)"
-IMPL=0
-if [ $RC3 -eq 0 ]; then
-    stamp "layer tests with the BF16x3 epilogue as the library default"
-    ULTRA_UPDATE_IMPL=3 ULTRA_RSPMM_LIB=$WIN timeout 120 python -m pytest tests/test_layer_gpu.py -m gpu -x -q > gpurun_out/pytest_layer_impl3.log 2>&1
-    RCL=$?
-    stamp "layer impl3 rc=$RCL : $(tail -1 gpurun_out/pytest_layer_impl3.log)"
-    # adopt it for the bench line only if it is also faster at C2 size
-    IMPL=$(python - <<'EOF'
-import json
-try:
-    r = {d["impl"]: d for d in (json.loads(l) for l in open("gpurun_out/update_bf16x3.jsonl") if l.startswith("{"))}
-    ok = r[3]["ms_med"] < 0.97 * r[0]["ms_med"] and r[3]["max_abs_err_vs_fp64"] < 2e-5
-    print(3 if ok else 0)
-except Exception:
-    print(0)
-EOF
-)
-    [ $RCL -eq 0 ] || IMPL=0
-fi
-stamp "bench.py with winner lib, update_impl=$IMPL"
-ULTRA_UPDATE_IMPL=$IMPL ULTRA_RSPMM_LIB=$WIN timeout 240 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-stamp "bench rc=$? : $(head -c 300 gpurun_out/bench_final.json)"
-if [ "$WIN" != "$PWD/ultra_b200/lib/libultra_rspmm.so" ]; then
+stamp "bench.py with the winner"
+ULTRA_RSPMM_LIB=$WIN timeout 240 python bench.py > gpurun_out/bench_winner.json 2> gpurun_out/bench_winner.err
+stamp "bench rc=$? : $(head -c 300 gpurun_out/bench_winner.json)"
+
+if [ "$WIN" != "$DEFAULT_LIB" ]; then
     stamp "ncu --set full of the winner's forward kernel"
     ULTRA_RSPMM_LIB=$WIN timeout 150 ncu --set full --clock-control none --import-source on -k regex:seg_reduce_kernel -s 3 -c 1 \
-        -f -o gpurun_out/r01_fwd_v6 python tools/kbench.py --alphas 1.0 > gpurun_out/ncu_fwd_v6.log 2>&1
-    stamp "ncu rc=$?"
-fi
-if [ "$IMPL" = "3" ]; then
-    stamp "ncu --set full of the BF16x3 epilogue"
-    timeout 120 ncu --set full --clock-control none --import-source on -k regex:update_tc3_kernel -s 2 -c 1 \
-        -f -o gpurun_out/r01_update_v9 python tools/update_bench.py 3 > gpurun_out/ncu_update_v9.log 2>&1
+        -f -o gpurun_out/fwd_winner python tools/kbench.py --alphas 1.0 > gpurun_out/ncu_fwd_winner.log 2>&1
     stamp "ncu rc=$?"
 fi
 stamp "done"
