@@ -4,7 +4,7 @@ Parent: ``python tools/ab_bench.py [--out FILE]`` runs one child per library (``
 per (library, case) and a final ``{"winner": ...}`` line: the library with the lowest summed forward time over the cases
 whose outputs are bit-identical to the default build's (same arithmetic order, so they must be).
 Child: ``--child`` times C2 (FB15k-237 scale, 128 heads) forward on the Zipf and the uniform graph, one backward, and a
-max x add forward at 32 heads, and prints an int64 checksum of every result.
+max x add forward at 32 heads, and the fused layer epilogue at C2 size, and prints an int64 checksum of every result.
 """
 import argparse
 import json
@@ -64,6 +64,21 @@ def child():
             rec.update({"bwd_ms": round(med, 4), "ig_sum": checksum(ig), "rg_sum": checksum(rg)})
         print(json.dumps(rec), flush=True)
         del plan
+    # fused layer epilogue at C2 size (library default implementation of ultra_nbfnet_update_f32)
+    from ultra_b200.fused import nbfnet_update
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(128, 64).to(d)
+    ln = torch.nn.LayerNorm(64).to(d)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+        M = 128 * 14541
+        x = torch.randn(M, 64, device=d)
+        u = torch.randn(M, 64, device=d) * 3
+        got = nbfnet_update(x, u, lin, ln, relu=True, shortcut=True)
+        med, best = time_fn(lambda: nbfnet_update(x, u, lin, ln, relu=True, shortcut=True), warmup=3, iters=15)
+    print(json.dumps({"case": "update", "upd_ms": round(med, 4), "upd_ms_min": round(best, 4),
+                      "upd_sum": checksum(got)}), flush=True)
 
 
 def main():
@@ -97,11 +112,12 @@ def main():
             lines.append({"lib": name, "error": err})
         print("\n".join(json.dumps(l) for l in lines[-(len(recs) + (1 if err else 0)):]), flush=True)
     base = results.get("default") or []
-    sums = lambda recs: [[r.get(k) for k in ("fwd_sum", "ig_sum", "rg_sum")] for r in recs]  # noqa: E731
+    sums = lambda recs: [[r.get(k) for k in ("fwd_sum", "ig_sum", "rg_sum", "upd_sum")] for r in recs]  # noqa: E731
     score = {}
     for name, recs in results.items():
         if len(recs) == len(base) and base and sums(recs) == sums(base):
-            score[name] = round(sum(r["fwd_ms"] for r in recs) + 0.25 * sum(r.get("bwd_ms", 0.0) for r in recs), 4)
+            score[name] = round(sum(r.get("fwd_ms", 0.0) + 0.25 * r.get("bwd_ms", 0.0) + r.get("upd_ms", 0.0)
+                                    for r in recs), 4)
     winner = min(score, key=score.get) if score else "default"
     # a variant must win by more than run-to-run noise to displace the default
     if winner != "default" and "default" in score and score[winner] > 0.985 * score["default"]:

@@ -12,29 +12,44 @@ from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ultra_b200 import build as lib_build  # noqa: E402
 
+# name -> {source file: extra nvcc flags}; sources not named reuse the default build's objects.
 # Round-1 A/B (profiles/r01_ab_meta_variants.jsonl) made PAD=16 + PAIR=1 the default; "nopadpair" is the old build.
-# Queued for the next session (ptxas, 64-register cap: U=4 24 B of spills, U=6 104 B with one LDL per loop iteration,
-# U=8 312 B, of which the unit-weight path - the only one ULTRA uses - holds 116 B: 3 LDL + 1 STL per loop iteration
-# next to 8 LDG.128; the non-unit-weight path stays at 4): more row gathers in flight per lane - the forward kernel is latency-bound (long_scoreboard), so bytes in
-# flight are what count.  U=6 does not divide the 64 staged entries, so it needs the clamped single loads (PAIR=0).
+# Queued for the next session:
+#  * forward / by-column kernels (ptxas, 64-register cap: U=4 24 B of spills, U=6 104 B with one LDL per loop iteration,
+#    U=8 312 B, of which the unit-weight path - the only one ULTRA uses - holds 116 B: 3 LDL + 1 STL per loop iteration
+#    next to 8 LDG.128; the non-unit-weight path stays at 4): more row gathers in flight per lane - the kernel is
+#    latency-bound (long_scoreboard), so bytes in flight are what count.  U=6 does not divide the 64 staged entries,
+#    so it needs the clamped single loads (PAIR=0).
+#  * BF16x3 layer epilogue: where the next tile's loads are issued (ULTRA_TC3_PREFETCH, see nbfnet_update_tc3.cu): the
+#    ncu source page shows the membar of fence.proxy.async waiting for the loads issued just before it.
+API, TC3 = "rspmm_api.cu", "nbfnet_update_tc3.cu"
 VARIANTS = {
-    "nopadpair": ["-DULTRA_META_PAD=0", "-DULTRA_META_PAIR=0"],
-    "unroll6": ["-DULTRA_FWD_UNROLL=6", "-DULTRA_FWD_UNROLL_W=4", "-DULTRA_META_PAIR=0"],
-    "unroll8": ["-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"],
+    "nopadpair": {API: ["-DULTRA_META_PAD=0", "-DULTRA_META_PAIR=0"]},
+    "unroll6": {API: ["-DULTRA_FWD_UNROLL=6", "-DULTRA_FWD_UNROLL_W=4", "-DULTRA_META_PAIR=0"]},
+    "unroll8": {API: ["-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"]},
+    "tc3pf1": {TC3: ["-DULTRA_TC3_PREFETCH=1"]},
+    "tc3pf2": {TC3: ["-DULTRA_TC3_PREFETCH=2"]},
 }
 OUT_DIR = os.path.join(lib_build.LIB_DIR, "variants")
 
 
 def build_variant(name):
     os.makedirs(OUT_DIR, exist_ok=True)
-    obj = os.path.join(OUT_DIR, "rspmm_api_%s.o" % name)
     so = os.path.join(OUT_DIR, "libultra_rspmm_%s.so" % name)
-    src = os.path.join(lib_build.CSRC, "rspmm_api.cu")
-    subprocess.run([lib_build.NVCC] + lib_build.NVCC_FLAGS + VARIANTS[name] + ["-c", src, "-o", obj], check=True)
-    others = [os.path.join(lib_build.LIB_DIR, s.replace(".cu", ".o")) for s in lib_build.SOURCES if s != "rspmm_api.cu"]
-    subprocess.run([lib_build.NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so, obj] + others,
-                   check=True)
-    os.remove(obj)
+    objs, tmp = [], []
+    for src in lib_build.SOURCES:
+        flags = VARIANTS[name].get(src)
+        if flags is None:
+            objs.append(os.path.join(lib_build.LIB_DIR, src.replace(".cu", ".o")))
+            continue
+        obj = os.path.join(OUT_DIR, "%s_%s.o" % (src.replace(".cu", ""), name))
+        subprocess.run([lib_build.NVCC] + lib_build.NVCC_FLAGS + flags + ["-c", os.path.join(lib_build.CSRC, src), "-o", obj],
+                       check=True)
+        objs.append(obj)
+        tmp.append(obj)
+    subprocess.run([lib_build.NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs, check=True)
+    for obj in tmp:
+        os.remove(obj)
     return so
 
 

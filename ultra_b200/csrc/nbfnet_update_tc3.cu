@@ -23,6 +23,15 @@
 
 #include "../../include/ultra_rspmm.h"
 
+#ifndef ULTRA_TC3_PREFETCH
+// Where the NEXT tile's global loads are issued inside a K-chunk step.  0 (default, the measured build): right after the
+// operand stores, i.e. BEFORE fence.proxy.async (SASS: MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S) and the CTA barrier.  The ncu
+// source page of that build (profiles/r01_ncu_v9_update_bf16x3_summary.md) puts the long_scoreboard stalls exactly on
+// that FENCE and BAR.SYNC and the barrier stalls on the branch behind them: the membar waits for the just-issued loads,
+// which puts a DRAM round trip on the critical path of every chunk step.  1: issue them after the barrier of the same
+// step; 2: issue all four chunks after the last step's barrier (the epilogue covers the latency).  To be A/B-measured.
+#define ULTRA_TC3_PREFETCH 0
+#endif
 #ifndef ULTRA_POLL_NS
 #define ULTRA_POLL_NS 64  // sleep between failed mbarrier polls
 #endif
@@ -183,8 +192,15 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
         pre[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live && row < M) {
             const float *src = col < kOut ? x + row * kOut + col : u + row * kOut + (col - kOut);
+#if ULTRA_TC3_PREFETCH == 0
             pre[2 * c] = __ldg(reinterpret_cast<const float4 *>(src));
             pre[2 * c + 1] = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+#else  // ordinary (coherent) loads: ptxas hoists ld.global.nc back above the membar + barrier (SASS identical to variant 0)
+            asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pre[2 * c].x), "=f"(pre[2 * c].y),
+                         "=f"(pre[2 * c].z), "=f"(pre[2 * c].w) : "l"(src) : "memory");
+            asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pre[2 * c + 1].x), "=f"(pre[2 * c + 1].y),
+                         "=f"(pre[2 * c + 1].z), "=f"(pre[2 * c + 1].w) : "l"(src + 4) : "memory");
+#endif
         }
     };
 #pragma unroll
@@ -211,10 +227,20 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
                     *reinterpret_cast<uint4 *>(dst + kATermBytes) = c1;
                     *reinterpret_cast<uint4 *>(dst + 2 * kATermBytes) = c2;
                 }
+#if ULTRA_TC3_PREFETCH == 0
                 fetch_chunk(tile + step, c, i + 1 < n_my);  // next tile's rows of this chunk: in flight for a whole tile
+#endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
+#if ULTRA_TC3_PREFETCH == 1
+                fetch_chunk(tile + step, c, i + 1 < n_my);  // after the membar + barrier, so neither waits for these loads
+#elif ULTRA_TC3_PREFETCH == 2
+                if (c == kStages - 1) {  // all of the next tile's rows at once: the epilogue below covers their latency
+#pragma unroll
+                    for (int cc = 0; cc < kStages; cc++) fetch_chunk(tile + step, cc, i + 1 < n_my);
+                }
+#endif
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + (uint32_t)(i & 1) * kAccStride;
