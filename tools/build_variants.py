@@ -33,12 +33,22 @@ VARIANTS = {
 OUT_DIR = os.path.join(lib_build.LIB_DIR, "variants")
 
 
+def flags_of(name):
+    """'a+b' combines the per-source flags of variants a and b (the forward and the epilogue experiments are orthogonal)."""
+    merged = {}
+    for part in name.split("+"):
+        for src, flags in VARIANTS[part].items():
+            merged[src] = merged.get(src, []) + flags
+    return merged
+
+
 def build_variant(name):
     os.makedirs(OUT_DIR, exist_ok=True)
     so = os.path.join(OUT_DIR, "libultra_rspmm_%s.so" % name)
     objs, tmp = [], []
+    per_source = flags_of(name)
     for src in lib_build.SOURCES:
-        flags = VARIANTS[name].get(src)
+        flags = per_source.get(src)
         if flags is None:
             objs.append(os.path.join(lib_build.LIB_DIR, src.replace(".cu", ".o")))
             continue
@@ -55,7 +65,7 @@ def build_variant(name):
 
 if __name__ == "__main__":
     lib_build.build()
-    names = sys.argv[1:] or list(VARIANTS)
+    names = sys.argv[1:] or list(VARIANTS) + ["unroll8+tc3pf1", "unroll8+tc3pf2"]
     with ThreadPoolExecutor(len(names)) as ex:
         for so in ex.map(build_variant, names):
             print(so)
