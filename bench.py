@@ -16,6 +16,7 @@ whole batch (the call GeneralizedRelationalConv.message_and_aggregate makes, /ro
               HBM copy peak in MEASURED_PEAKS.json
   backward  : (extra, SURVEY 8d iii) ms per ultra_rspmm_backward call on the same workload; plan_build_ms also carries
               forward_incl_plan_build_ms (SURVEY 8d ii: the reference wrapper sorts on every call)
+  cpu_baseline.parity : the timed workload's GPU output against the reference CPU kernel's, same tensors
   cpu_baseline / --impl reference : the reference's own CPU kernel (oracle/_ref, built from /root/reference by
               oracle/build_ref.py) on this box's host cores
 
@@ -337,7 +338,13 @@ def main():
             "nbfnet_layer": layer_info,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            try:  # the timed step's own output, brought to the host for the parity check against the reference kernel
+                step()
+                torch.cuda.synchronize()
+                gpu_out = out_d.cpu()
+            except Exception:  # noqa: BLE001 - the parity extra must never fail the run
+                gpu_out = None
+            line["cpu_baseline"] = cpu_baseline(wl, gpu_out)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -410,7 +417,23 @@ def bench_layer(wl, device, world, rank):
     return info
 
 
-def cpu_baseline(wl):
+def parity_against(ref_out, gpu_out):
+    """SURVEY 8d "parity check in the same run": the GPU forward of the timed workload against the reference CPU kernel's
+    output on the same tensors, north-star tolerance 1e-5 relative (to max|ref|)."""
+    try:
+        if gpu_out is None:
+            return {"checked": False, "why": "no GPU output"}
+        scale = float(ref_out.abs().max())
+        err = float((gpu_out - ref_out).abs().max())
+        return {"checked": True, "max_abs_err": err, "max_abs_ref": scale, "rel_to_max": err / scale if scale else 0.0,
+                "tolerance": 1e-5, "ok": bool(err <= 1e-5 * scale),
+                "what": "ultra_rspmm_forward output of the timed workload (all %d x %d elements) vs "
+                        "rspmm_add_mul_forward_cpu of the reference" % tuple(ref_out.shape)}
+    except Exception as exc:  # noqa: BLE001
+        return {"checked": False, "why": repr(exc)}
+
+
+def cpu_baseline(wl, gpu_out=None):
     """Reference CPU kernel (oracle/_ref) on this box's host cores, bounded sample: full C2 batch, 1 warm-up + 3 reps."""
     from oracle import ref
     import oracle
@@ -429,7 +452,7 @@ def cpu_baseline(wl):
     ei, et, w, rel, x = wl["ei"], wl["et"], wl["w"], wl["rel"], wl["x"]
     sei, stt, sw, _ = oracle.sort_edges(ei.numpy(), et.numpy(), w.numpy())
     tei, ttt, tw = torch.from_numpy(sei), torch.from_numpy(stt), torch.from_numpy(sw)
-    ref.ref_forward("add", "mul", tei, ttt, tw, rel, x)
+    parity = parity_against(ref.ref_forward("add", "mul", tei, ttt, tw, rel, x), gpu_out)  # doubles as the warm-up
     ts, tw_ = [], []
     for _ in range(3):
         t0 = time.perf_counter()
@@ -450,7 +473,7 @@ def cpu_baseline(wl):
     return {"value": wl["E"] / min(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
             "sample": "full C2 batch (128 heads, D=8192), kernel call on pre-sorted edges, min of 3 after 1 warm-up",
             "wrapper_value": wl["E"] / min(tw_), "kernel_ms": 1e3 * min(ts), "wrapper_ms": 1e3 * min(tw_),
-            "cpu": cpu_model, "os_cpu_count": cores}
+            "cpu": cpu_model, "os_cpu_count": cores, "parity": parity}
 
 
 if __name__ == "__main__":
