@@ -51,6 +51,9 @@ const char *ultra_rspmm_version(void);
  * (nbfnet_update_tc2.cu); 1 = plain fp32 FFMA kernel; 2 = the first, non-pipelined tcgen05 kernel
  * (nbfnet_update_tc.cu); -1 restores the library default (which ULTRA_UPDATE_IMPL=0..3 in the environment overrides
  * at load time).  "host_copy_split": row blocks per slab copy in forward_host.
+ * "item_edges": edges per work item of the plans built (and workspaces sized) afterwards: 64 (default, the kernels'
+ * staging capacity), 32 or 16 - finer items for calls so small that 64-edge items leave a nearly empty second wave of
+ * warps (experimental: cutter invariants are CPU-tested, GPU validation pending).
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a
  * 16-byte vector reduction at L2 (red.global.add.v4.f32), like the reference's atomicAdd backward (rspmm.cu:198-209):

@@ -5,14 +5,14 @@ import ctypes
 import numpy as np
 import pytest
 
-ITEM_EDGES = 64
 MERGED = 1 << 30
 
 
-def cut(seg_ptr):
+def cut(seg_ptr, ITEM_EDGES=64):
     from ultra_b200 import build, _capi
     build.build()
     lib = _capi.lib()
+    _capi.set_tunable("item_edges", ITEM_EDGES)
     seg_ptr = np.ascontiguousarray(seg_ptr, dtype=np.int32)
     S = len(seg_ptr) - 1
     E = int(seg_ptr[-1])
@@ -25,6 +25,7 @@ def cut(seg_ptr):
     rc = lib.ultra_rspmm_debug_cut_items(p(seg_ptr), S, p(items), cap, ctypes.byref(n[0]), p(fix), max(S, 1),
                                          ctypes.byref(n[1]), ctypes.byref(n[2]), ctypes.byref(n[3]), p(nonempty), S + 1,
                                          ctypes.byref(n[4]))
+    _capi.set_tunable("item_edges", 64)
     assert rc == 0, lib.ultra_rspmm_last_error()
     return (items[:n[0].value], fix[:n[1].value], n[2].value, n[3].value, nonempty[:n[4].value])
 
@@ -41,11 +42,13 @@ def degrees_cases():
     yield "relation-graph like", np.full(474, 1896)
 
 
+@pytest.mark.parametrize("ITEM_EDGES", [64, 32, 16], ids=["items64", "items32", "items16"])
 @pytest.mark.parametrize("name,deg", list(degrees_cases()), ids=[n for n, _ in degrees_cases()])
-def test_cut_items_invariants(name, deg):
+def test_cut_items_invariants(name, deg, ITEM_EDGES):
+    """ITEM_EDGES = the `item_edges` tunable: 64 is the default, 32 / 16 cut finer items for very small calls."""
     seg_ptr = np.concatenate([[0], np.cumsum(deg)])
     S, E = len(deg), int(seg_ptr[-1])
-    items, fix, nlong, nslots, nonempty = cut(seg_ptr)
+    items, fix, nlong, nslots, nonempty = cut(seg_ptr, ITEM_EDGES)
     assert len(items) % 4 == 0
     # every edge is covered exactly once
     cover = np.zeros(E + 1, np.int64)

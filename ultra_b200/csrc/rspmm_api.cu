@@ -275,7 +275,11 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl, bwd_fused_relgrad)");
+    if (n == "item_edges") {
+        if (set_item_edges(value)) { set_error("set_tunable: item_edges must be 64 (default), 32 or 16"); return 1; }
+        return 0;
+    }
+    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl, bwd_fused_relgrad, item_edges)");
     return 1;
 }
 

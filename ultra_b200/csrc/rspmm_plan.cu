@@ -7,6 +7,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <vector>
 
@@ -24,15 +25,20 @@ inline int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     while ((int64_t(1) << b) < n) b++;
     return b;
 }
+// Edges per work item (tunable "item_edges": 64 = kItemEdges, the kernels' staging capacity and the default; 32 / 16
+// cut finer items for calls so small that 64-edge items leave a second, nearly empty wave of warps - WN18RR x 4 heads
+// is 344 work units on 296 CTAs).  Read when the workspace is sized AND when the plan is built; a plan built with a
+// workspace sized for a coarser setting fails the size check instead of overflowing.
+std::atomic<int> g_item_edges{kItemEdges};
 // whole items <= 2E/L+1; chunks <= E/L + #long with #long <= E/L
-inline int64_t max_items(int64_t E) { return 4 * ((E + kItemEdges - 1) / kItemEdges) + 8; }
+inline int64_t max_items(int64_t E, int L) { return 4 * ((E + L - 1) / L) + 8; }
 
 struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
 };
 
-WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
+WsLayout make_layout(int64_t N, int64_t E, int64_t R, int item_edges) {
     WsLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(std::max<size_t>(bytes, 16)); return o; };
@@ -42,7 +48,7 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
         L.eid[o] = take((size_t)E * 4);
         L.seg_ptr[o] = take((size_t)(S[o] + 1) * 4);
         L.nonempty[o] = take((size_t)(S[o] + 1) * 4);
-        L.items[o] = take((size_t)max_items(E) * 16);
+        L.items[o] = take((size_t)max_items(E, item_edges) * 16);
         L.fix[o] = take((size_t)std::max<int64_t>(S[o], 1) * 16);
         L.w[o] = take((size_t)E * 8);
     }
@@ -130,9 +136,9 @@ __global__ void build_meta_kernel(int order, const unsigned long long *__restric
 // items longest first, so the 4 items a warp walks in lock-step have (nearly) equal lengths.
 // fix list: long segments first, then empty segments.
 void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vector<int> &nonempty,
-               std::vector<int4> &fix, int &num_slots, int &num_fix_long) {
+               std::vector<int4> &fix, int &num_slots, int &num_fix_long, const int kItemEdges) {  // shadows the constant
     const int S = (int)ptr.size() - 1;
-    constexpr int kGroupEdges = kItemEdges * kSubPerWarp;
+    const int kGroupEdges = kItemEdges * kSubPerWarp;
     std::vector<int4> groups, rest, fix_empty;
     items.clear(); nonempty.clear(); fix.clear();
     num_slots = 0;
@@ -176,7 +182,13 @@ void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vecto
 
 }  // namespace
 
-size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layout(N, E, R).total; }
+size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layout(N, E, R, g_item_edges.load()).total; }
+
+int set_item_edges(int edges) {
+    if (edges != 16 && edges != 32 && edges != kItemEdges) return 1;
+    g_item_edges.store(edges);
+    return 0;
+}
 
 // Host-only access to the work-item cutter (pure CPU; used by the CPU test-suite to check its invariants).
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
@@ -186,7 +198,7 @@ int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t item
     std::vector<int4> items, fix;
     std::vector<int> nonempty;
     int slots = 0, nlong = 0;
-    cut_items(ptr, items, nonempty, fix, slots, nlong);
+    cut_items(ptr, items, nonempty, fix, slots, nlong, g_item_edges.load());
     if ((int64_t)items.size() > items_cap || (int64_t)fix.size() > fix_cap || (int64_t)nonempty.size() > nonempty_cap) {
         set_error("cut_items_host: output capacity too small");
         return 1;
@@ -206,7 +218,8 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         set_error("plan_build: num_node / num_edge / num_relation out of int32 range");
         return 1;
     }
-    const WsLayout L = make_layout(N, E, R);
+    const int item_edges = g_item_edges.load();  // one value for the size check and the cutter
+    const WsLayout L = make_layout(N, E, R, item_edges);
     if (workspace_bytes < L.total || (workspace == nullptr && L.total > 0)) {
         set_error("plan_build: workspace too small");
         return 1;
@@ -299,8 +312,8 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         h_ptr.resize((size_t)S[o] + 1);
         CUDA_TRY(cudaMemcpyAsync(h_ptr.data(), so.seg_ptr, (size_t)(S[o] + 1) * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        cut_items(h_ptr, items, nonempty, fix, so.num_slots, so.num_fix_long);
-        if ((int64_t)items.size() > max_items(E)) {
+        cut_items(h_ptr, items, nonempty, fix, so.num_slots, so.num_fix_long, item_edges);
+        if ((int64_t)items.size() > max_items(E, item_edges)) {
             delete plan;
             set_error("plan_build: item bound exceeded");
             return 4;

@@ -44,6 +44,8 @@ namespace ultra {
 void set_error(const std::string &msg);
 void set_update_impl(int v);  // nbfnet_update.cu: 0 = tensor-core epilogue, 1 = FFMA epilogue
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
+// tunable "item_edges": 64 (default), 32 or 16 edges per work item for plans built afterwards; returns 1 on a bad value
+int set_item_edges(int edges);
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
                    int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
                    int64_t nonempty_cap, int *num_nonempty);
