@@ -46,6 +46,26 @@ def degrees_cases():
 @pytest.mark.parametrize("name,deg", list(degrees_cases()), ids=[n for n, _ in degrees_cases()])
 def test_cut_items_invariants(name, deg, ITEM_EDGES):
     """ITEM_EDGES = the `item_edges` tunable: 64 is the default, 32 / 16 cut finer items for very small calls."""
+    check_invariants(deg, ITEM_EDGES)
+
+
+@pytest.mark.parametrize("ITEM_EDGES", [64, 32, 16], ids=["items64", "items32", "items16"])
+def test_cut_items_invariants_randomized(ITEM_EDGES):
+    """Seeded random degree sequences: mixtures of empty, short, exactly-full, long and very long segments."""
+    rng = np.random.default_rng(100 + ITEM_EDGES)
+    for _ in range(25):
+        S = int(rng.integers(1, 400))
+        kind = rng.integers(0, 5, S)
+        deg = np.where(kind == 0, 0, np.where(kind == 1, rng.integers(1, ITEM_EDGES, S),
+                       np.where(kind == 2, ITEM_EDGES * rng.integers(1, 6, S),
+                                np.where(kind == 3, rng.integers(ITEM_EDGES, 6 * ITEM_EDGES, S),
+                                         rng.integers(1, 3, S)))))
+        if rng.random() < 0.3:
+            deg[int(rng.integers(0, S))] = int(rng.integers(1000, 20000))
+        check_invariants(deg.astype(np.int64), ITEM_EDGES)
+
+
+def check_invariants(deg, ITEM_EDGES):
     seg_ptr = np.concatenate([[0], np.cumsum(deg)])
     S, E = len(deg), int(seg_ptr[-1])
     items, fix, nlong, nslots, nonempty = cut(seg_ptr, ITEM_EDGES)
