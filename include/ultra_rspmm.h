@@ -42,18 +42,12 @@ typedef struct ultra_rspmm_plan ultra_rspmm_plan; /* opaque host object */
 const char *ultra_rspmm_version(void);
 
 /*
- * Process-wide launch tunables.  "sm_limit": size the persistent grids for this many SMs (0 = all) so that a
- * concurrent NCCL collective (the overlapped all-gather of node states, ultra_b200/shard.py) finds free SMs.
+ * Process-wide launch tunables (experiment knobs; nothing on the data path depends on them being set).
  * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
- * "update_impl" selects the kernel behind ultra_nbfnet_update_f32: 3 (library default) = tensor cores, pipelined tcgen05
- * kernel with a BF16x3 operand split on kind::f16 (nbfnet_update_tc3.cu, fp32-level accuracy: 3.2e-6 max abs error
- * against fp64 on outputs of magnitude 7); 0 = the same pipeline with a 3xTF32 split on kind::tf32
- * (nbfnet_update_tc2.cu); 1 = plain fp32 FFMA kernel; 2 = the first, non-pipelined tcgen05 kernel
- * (nbfnet_update_tc.cu); -1 restores the library default (which ULTRA_UPDATE_IMPL=0..3 in the environment overrides
- * at load time).  "host_copy_split": row blocks per slab copy in forward_host.
- * "item_edges": edges per work item of the plans built (and workspaces sized) afterwards: 64 (default, the kernels'
- * staging capacity), 32 or 16 - finer items for calls so small that 64-edge items leave a nearly empty second wave of
- * warps (experimental: cutter invariants are CPU-tested, GPU validation pending).
+ * "host_copy_split": row blocks per slab copy in forward_host.
+ * "item_edges": edges per work item of the plans built (and workspaces sized) afterwards: 64 (the kernels' staging
+ * capacity), 32 or 16 - finer items for calls so small that 64-edge items leave a nearly empty second wave of warps;
+ * 0 (default) = chosen per plan from the edge count.
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a
  * 16-byte vector reduction at L2 (red.global.add.v4.f32), like the reference's atomicAdd backward (rspmm.cu:198-209):
@@ -62,7 +56,6 @@ const char *ultra_rspmm_version(void);
  * reductions collide on hot relations); min/max x mul 14.0 -> 5.5 / 8.6 -> 6.1 ms; add x add is faster two-pass.
  */
 int ultra_rspmm_set_tunable(const char *name, int value);
-int ultra_rspmm_get_sm_limit(void);
 
 /*
  * Host-only (no GPU needed): run the plan's work-item cutter on a CSR segment pointer (num_seg + 1 ints) and return
@@ -95,6 +88,14 @@ int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_inde
                            size_t workspace_bytes, void *stream);
 
 void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan);
+
+/*
+ * Per-plan SM reservation: size this plan's persistent grids for `sm_limit` SMs (0 = all) so that a concurrent NCCL
+ * collective (the overlapped all-gather of node states, ultra_b200/shard.py) finds free SMs.  Host-side field of the
+ * plan; takes effect for launches issued afterwards.  (Round 1 had a process-global tunable here; a plan is the unit
+ * a sharded runner owns, so two runners / streams can no longer disturb each other.)
+ */
+int ultra_rspmm_plan_set_sm_limit(ultra_rspmm_plan *plan, int sm_limit);
 
 /* 1 if the caller's edge order was already sorted by the reference key (rspmm.py:15-17), else 0. */
 int ultra_rspmm_plan_input_sorted(const ultra_rspmm_plan *plan);
@@ -185,11 +186,14 @@ int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_o
  *   x, u, out : device (num_rows, 64) row-major, num_rows = heads * nodes (the (B, N, 64) layer state as is)
  *   weight_t  : device (128, 64) = nn.Linear.weight transposed;  bias / ln_gamma / ln_beta : device (64) or NULL
  * Only in_dim == 128, out_dim == 64 is implemented (sum / mean / max aggregation at ULTRA's dim 64); anything else
- * returns an error and the caller keeps its own epilogue.
+ * returns an error and the caller keeps its own epilogue.  One implementation: pipelined tcgen05 kernel with a BF16x3
+ * operand split (fp32-level accuracy: 3.2e-6 max abs error against fp64 on outputs of magnitude 7).
+ * sm_limit: persistent CTAs to launch at most (0 = one per SM), see ultra_rspmm_plan_set_sm_limit.
  */
 int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_t, const float *bias,
                             const float *ln_gamma, const float *ln_beta, float *out, int64_t num_rows, int64_t in_dim,
-                            int64_t out_dim, float ln_eps, int layer_norm, int relu, int shortcut, void *stream);
+                            int64_t out_dim, float ln_eps, int layer_norm, int relu, int shortcut, int sm_limit,
+                            void *stream);
 
 #ifdef __cplusplus
 }

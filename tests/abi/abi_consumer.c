@@ -18,8 +18,8 @@ int main(void) {
         fprintf(stderr, "implausible workspace size %zu\n", ws);
         return 2;
     }
-    if (ultra_rspmm_set_tunable("sm_limit", 140) != 0 || ultra_rspmm_get_sm_limit() != 140) return 3;
-    if (ultra_rspmm_set_tunable("sm_limit", 0) != 0) return 4;
+    if (ultra_rspmm_set_tunable("l2_percent", 25) != 0) return 3;
+    if (ultra_rspmm_plan_set_sm_limit(NULL, 140) == 0) return 4; /* null plan is an error code, not a crash */
     /* errors come back as codes plus a message, never as C++ exceptions */
     if (ultra_rspmm_set_tunable("no_such_knob", 1) == 0) return 5;
     if (strstr(ultra_rspmm_last_error(), "unknown tunable") == NULL) return 6;

@@ -147,13 +147,11 @@ def test_rspmm_heads_equals_flat_path(cuda_device, sum, mul, dtype, d, with_boun
         assert torch.equal(b1.grad, b2.grad)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["tcgen05_pipelined", "ffma", "tcgen05_serial", "tcgen05_bf16x3"])
+@pytest.mark.parametrize("sm_limit", [0, 100])
 @pytest.mark.parametrize("layer_norm,relu,shortcut", [(True, True, True), (True, True, False), (False, True, True),
                                                       (True, False, False)])
-def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
-    from ultra_b200 import _capi
+def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, sm_limit):
     from ultra_b200.fused import nbfnet_update
-    _capi.set_tunable("update_impl", impl)
     dev = cuda_device
     torch.manual_seed(5)
     lin = torch.nn.Linear(128, 64).to(dev)
@@ -165,7 +163,7 @@ def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
     for M in (1, 127, 128, 1000, 128 * 300 + 17):
         x, u = torch.randn(M, 64, device=dev), torch.randn(M, 64, device=dev) * 3
         with torch.no_grad():
-            got = nbfnet_update(x, u, lin, ln, relu=relu, shortcut=shortcut)
+            got = nbfnet_update(x, u, lin, ln, relu=relu, shortcut=shortcut, sm_limit=sm_limit)
             ref = lin(torch.cat([x, u], -1).double().float())
             ref = torch.nn.functional.linear(torch.cat([x, u], -1).double(), lin.weight.double(), lin.bias.double())
             if ln is not None:
@@ -175,7 +173,6 @@ def test_nbfnet_update_kernel(cuda_device, layer_norm, relu, shortcut, impl):
             if shortcut:
                 ref = ref + x.double()
         torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=2e-5)
-    _capi.set_tunable("update_impl", -1)
 
 
 @pytest.mark.parametrize("message,aggregate", [("distmult", "sum"), ("transe", "max"), ("distmult", "mean")])

@@ -97,9 +97,6 @@ def test_cuda_matches_oracle(cuda_device, shape, sum, mul):
     check_against(sum, mul, ours, expected)
 
 
-@pytest.mark.skipif(os.environ.get("ULTRA_TEST_EXPERIMENTAL") != "1",
-                    reason="finer work items (tunable item_edges = 32 / 16) are built and CPU-tested (cutter invariants) "
-                           "but not yet validated on a GPU: run with ULTRA_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("item_edges", [32, 16])
 @pytest.mark.parametrize("shape", SHAPES[:3] + SHAPES[4:6] + SHAPES[8:], ids=lambda s: "N%d_E%d_D%d" % (s[1], s[2], s[4]))
 @pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "add"), ("min", "mul")])

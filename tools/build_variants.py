@@ -20,9 +20,9 @@ from ultra_b200 import build as lib_build  # noqa: E402
 #    next to 8 LDG.128; the non-unit-weight path stays at 4): more row gathers in flight per lane - the kernel is
 #    latency-bound (long_scoreboard), so bytes in flight are what count.  U=6 does not divide the 64 staged entries,
 #    so it needs the clamped single loads (PAIR=0).
-#  * BF16x3 layer epilogue: where the next tile's loads are issued (ULTRA_TC3_PREFETCH, see nbfnet_update_tc3.cu): the
+#  * BF16x3 layer epilogue: where the next tile's loads are issued (ULTRA_TC3_PREFETCH, see nbfnet_update.cu): the
 #    ncu source page shows the membar of fence.proxy.async waiting for the loads issued just before it.
-API, TC3 = "rspmm_api.cu", "nbfnet_update_tc3.cu"
+API, TC3 = "rspmm_api.cu", "nbfnet_update.cu"
 VARIANTS = {
     "nopadpair": {API: ["-DULTRA_META_PAD=0", "-DULTRA_META_PAIR=0"]},
     "unroll6": {API: ["-DULTRA_FWD_UNROLL=6", "-DULTRA_FWD_UNROLL_W=4", "-DULTRA_META_PAIR=0"]},

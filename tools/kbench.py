@@ -44,8 +44,6 @@ def main():
     lib = _capi.lib()
     if args.l2_percent:
         _capi.set_tunable("l2_percent", args.l2_percent)
-    if args.sm_limit:
-        _capi.set_tunable("sm_limit", args.sm_limit)
     if args.item_edges:
         _capi.set_tunable("item_edges", args.item_edges)
     for alpha in [float(a) for a in args.alphas.split(",")]:
@@ -57,6 +55,8 @@ def main():
         x = torch.randn(N, D, device=d, generator=g)
         out = torch.empty_like(x)
         plan = GraphPlan(ei.to(d), et.to(d), N, R)
+        if args.sm_limit:
+            plan.set_sm_limit(args.sm_limit)
         scratch = plan.scratch(D, torch.float32)
         deg = torch.bincount(ei[0], minlength=N)
         print(json.dumps({"alpha": alpha, "N": N, "E": E, "R": R, "D": D, "max_deg": int(deg.max()),

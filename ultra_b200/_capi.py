@@ -18,7 +18,7 @@ SYMBOLS = {
     "ultra_rspmm_version": (ctypes.c_char_p, []),
     "ultra_rspmm_last_error": (ctypes.c_char_p, []),
     "ultra_rspmm_set_tunable": (_int, [ctypes.c_char_p, _int]),
-    "ultra_rspmm_get_sm_limit": (_int, []),
+    "ultra_rspmm_plan_set_sm_limit": (_int, [_vp, _int]),
     "ultra_rspmm_debug_cut_items": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ultra_rspmm_plan_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ultra_rspmm_plan_build": (_int, [ctypes.POINTER(_vp), _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
@@ -34,7 +34,7 @@ SYMBOLS = {
     "ultra_rspmm_backward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz,
                                           _vp]),
     "ultra_nbfnet_update_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float, _int, _int,
-                                       _int, _vp]),
+                                       _int, _int, _vp]),
     "ultra_rspmm_host_staging_bytes": (_sz, [_vp, _i64, _i64, _int]),
     "ultra_rspmm_forward_host": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
 }

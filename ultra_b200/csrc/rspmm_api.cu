@@ -29,8 +29,7 @@ namespace {
 constexpr size_t kMetaSmem = (size_t)kCtaWarps * kMetaStageBytes;  // 32 KB of per-warp metadata staging per CTA
 constexpr size_t kSlabSmemLimit = 78 * 1024;  // tiles in smem while 2 CTAs/SM (tiles + metadata + reserve) still fit in 227 KB
 
-// process-wide launch tunables (ultra_rspmm_set_tunable)
-std::atomic<int> g_sm_limit{0};          // 0 = use every SM; >0 = size persistent grids for this many SMs
+// process-wide launch tunables (ultra_rspmm_set_tunable); the SM reservation is per plan (ultra_rspmm_plan_set_sm_limit)
 std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
 std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy
 std::atomic<int> g_bwd_fused_relgrad{0}; // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
@@ -104,7 +103,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
     if (p.num_warp_items > 0) {
-        const int sm_limit = g_sm_limit.load();
+        const int sm_limit = plan->sm_limit;
         const int ctas = ((sm_limit > 0 && sm_limit < plan->sm_count) ? sm_limit : plan->sm_count) * 2;
         // items per warp per unit: 2 when that still leaves every CTA several units
         int ipw = 2;
@@ -266,12 +265,6 @@ const char *ultra_rspmm_version(void) { return "ultra_rspmm sm_100a 0.1.0"; }
 int ultra_rspmm_set_tunable(const char *name, int value) {
     if (name == nullptr) { set_error("set_tunable: null name"); return 1; }
     const std::string n(name);
-    if (n == "sm_limit") { g_sm_limit.store(value < 0 ? 0 : value); return 0; }
-    if (n == "update_impl") {
-        if (value < -1 || value > 3) { set_error("set_tunable: update_impl must be 0 (tcgen05 pipelined), 1 (FFMA), 2 (tcgen05 serial), 3 (tcgen05 BF16x3) or -1 (library default)"); return 1; }
-        set_update_impl(value);
-        return 0;
-    }
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
@@ -279,11 +272,15 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
         if (set_item_edges(value)) { set_error("set_tunable: item_edges must be 64 (default), 32 or 16"); return 1; }
         return 0;
     }
-    set_error("set_tunable: unknown tunable '" + n + "' (sm_limit, l2_percent, host_copy_split, update_impl, bwd_fused_relgrad, item_edges)");
+    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, item_edges)");
     return 1;
 }
 
-int ultra_rspmm_get_sm_limit(void) { return g_sm_limit.load(); }
+int ultra_rspmm_plan_set_sm_limit(ultra_rspmm_plan *plan, int sm_limit) {
+    if (plan == nullptr) { set_error("null plan"); return 1; }
+    plan->sm_limit = sm_limit < 0 ? 0 : sm_limit;
+    return 0;
+}
 
 int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items,
                                 int *fix_out, int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots,

@@ -36,13 +36,13 @@ struct ultra_rspmm_plan {
     int input_sorted = 0;
     int device = 0;
     int sm_count = 148;
+    int sm_limit = 0;            // 0 = size persistent grids for every SM; >0 = leave the rest to a concurrent collective
     size_t l2_bytes = 0;
     size_t smem_optin = 0;
 };
 
 namespace ultra {
 void set_error(const std::string &msg);
-void set_update_impl(int v);  // nbfnet_update.cu: 0 = tensor-core epilogue, 1 = FFMA epilogue
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
 // tunable "item_edges": 64 (default), 32 or 16 edges per work item for plans built afterwards; returns 1 on a bad value
 int set_item_edges(int edges);

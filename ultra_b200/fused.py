@@ -32,6 +32,14 @@ class _RSPMMHeadsFunction(autograd.Function):
             raise RuntimeError("rspmm_heads: relation must be (B, R, d) matching input (B, N, d)")
         if boundary is not None and boundary.shape != input.shape:
             raise RuntimeError("rspmm_heads: boundary must have the shape of input")
+        if relation.dtype != input.dtype or edge_weight.dtype != input.dtype or \
+                (boundary is not None and boundary.dtype != input.dtype):
+            raise RuntimeError("Expected tensors 'edge_weight', 'relation', 'input' to have the same type; got %s, %s, %s"
+                               % (edge_weight.dtype, relation.dtype, input.dtype))
+        devs = {t.device for t in (edge_index, edge_type, edge_weight, relation, input)}
+        if len(devs) != 1:
+            raise RuntimeError("Expected all tensors to be on the same device, got %s" % sorted(map(str, devs)))
+        # index dtype / shapes are validated by GraphPlan, the weight length by bind_weight
         plan = plan_cache.get(edge_index, edge_type, N, R)
         plan.bind_weight(edge_weight)
         rel_c, in_c = relation.detach().contiguous(), input.detach().contiguous()
@@ -91,8 +99,9 @@ def nbfnet_update_ok(x, u, linear, activation):
             and not torch.is_grad_enabled())
 
 
-def nbfnet_update(x, u, linear, layer_norm=None, relu=True, shortcut=False):
-    """One-pass layer epilogue (inference).  x, u: (..., 64) fp32 CUDA; returns a tensor of x's shape."""
+def nbfnet_update(x, u, linear, layer_norm=None, relu=True, shortcut=False, sm_limit=0):
+    """One-pass layer epilogue (inference).  x, u: (..., 64) fp32 CUDA; returns a tensor of x's shape.
+    sm_limit > 0 launches at most that many persistent CTAs (SMs left to a concurrent collective)."""
     lib = _capi.lib()
     xc, uc = x.contiguous(), u.contiguous()
     out = torch.empty_like(xc)
@@ -107,6 +116,6 @@ def nbfnet_update(x, u, linear, layer_norm=None, relu=True, shortcut=False):
                                          out.data_ptr(), rows, 128, 64,
                                          float(layer_norm.eps) if layer_norm is not None else 0.0,
                                          1 if layer_norm is not None else 0, 1 if relu else 0, 1 if shortcut else 0,
-                                         _stream_ptr(x.device))
+                                         int(sm_limit), _stream_ptr(x.device))
     _capi.check(rc, "ultra_nbfnet_update_f32")
     return out

@@ -62,8 +62,10 @@ class GeneralizedRelationalConv(nn.Module):
             update = self.message_and_aggregate_heads(edge_index, input, relation, boundary, edge_type, edge_weight,
                                                       size[0])
             if fused.nbfnet_update_ok(input, update, self.linear, self.activation):
+                from .plan import plan_cache
+                plan = plan_cache.get(edge_index, edge_type, input.shape[1], relation.shape[1])  # cache hit
                 return fused.nbfnet_update(input, update, self.linear, self.layer_norm,
-                                           relu=self.activation is not None, shortcut=shortcut)
+                                           relu=self.activation is not None, shortcut=shortcut, sm_limit=plan.sm_limit)
         else:
             update = self.message_and_aggregate(edge_index, input, relation, boundary, edge_type, edge_weight, size[0])
         output = self.update(update, input)
@@ -193,4 +195,10 @@ class GraphedBellmanFord:
         if relation is not None:
             self.static_relation.copy_(relation)
         self.graph.replay()
+        # the captured weight bind rewrote the plan's device weights: an eager call that bound another weight tensor
+        # before must re-bind (the Python-side key would otherwise still name that tensor)
+        from .plan import plan_cache
+        for entry in list(plan_cache._entries.values()):
+            if entry[1] is self.edge_index:
+                entry[0].invalidate_weight()
         return self.static_out

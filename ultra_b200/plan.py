@@ -19,12 +19,27 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _version(t):
+    """Version counter of a tensor for cache keys.  Inference tensors do not track one (reading `_version` raises), and
+    they cannot be mutated in place outside inference mode either, so a constant is a sound key for them.  Writes
+    through `.data` never bump the counter: callers that mutate edge tensors that way must call `plan_cache.clear()`
+    (or `GraphPlan.invalidate_weight()`)."""
+    return 0 if t.is_inference() else t._version
+
+
 class GraphPlan:
     """Device-resident sorted CSR views + work items of one relational graph (see include/ultra_rspmm.h)."""
 
     def __init__(self, edge_index, edge_type, num_node, num_relation):
         if edge_index.device.type != "cuda":
             raise RuntimeError("GraphPlan needs CUDA tensors (ultra_b200 has no CPU implementation of rspmm)")
+        if edge_index.dtype != torch.int64 or edge_type.dtype != torch.int64:
+            raise RuntimeError("expected scalar type Long for edge_index / edge_type, got %s / %s"
+                               % (edge_index.dtype, edge_type.dtype))
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2 or edge_type.dim() != 1 or \
+                edge_type.shape[0] != edge_index.shape[1] or edge_type.device != edge_index.device:
+            raise RuntimeError("GraphPlan: edge_index must be (2, E) and edge_type (E,) on the same device, got %s / %s"
+                               % (tuple(edge_index.shape), tuple(edge_type.shape)))
         lib = _capi.lib()
         self.device = edge_index.device
         self.num_node, self.num_relation = int(num_node), int(num_relation)
@@ -47,7 +62,26 @@ class GraphPlan:
         self.input_sorted = bool(lib.ultra_rspmm_plan_input_sorted(handle))
         self._scratch = None
         self._weight_key = None
-        self._lock = threading.Lock()
+        self.sm_limit = 0
+
+    def nbytes(self):
+        """Device bytes this plan pins (workspace + scratch + host-path staging), for the cache's byte budget."""
+        n = self.workspace.numel()
+        for name in ("_scratch", "_host_staging"):
+            t = getattr(self, name, None)
+            if t is not None:
+                n += t.numel()
+        return n
+
+    def set_sm_limit(self, sm_limit):
+        """Size this plan's persistent grids for `sm_limit` SMs (0 = all): leaves SMs to a concurrent collective."""
+        _capi.check(_capi.lib().ultra_rspmm_plan_set_sm_limit(self._handle, int(sm_limit)), "ultra_rspmm_plan_set_sm_limit")
+        self.sm_limit = int(sm_limit)
+
+    def invalidate_weight(self):
+        """Forget which weight tensor is bound (after something else rewrote the plan's device weights, e.g. a CUDA-graph
+        replay that captured a bind, or after the caller mutated the weight tensor through `.data`)."""
+        self._weight_key = None
 
     @property
     def handle(self):
@@ -65,13 +99,19 @@ class GraphPlan:
 
     def bind_weight(self, edge_weight):
         """Permute edge weights into the plan orders (no host sync); skipped if the same tensor is re-bound."""
-        key = (edge_weight.data_ptr(), edge_weight._version, edge_weight.dtype, tuple(edge_weight.shape),
+        if edge_weight.dim() != 1 or edge_weight.shape[0] != self.num_edge or edge_weight.dtype not in _DTYPE_ID:
+            raise RuntimeError("bind_weight: edge_weight must be a float32/float64 vector of length num_edge (%d), got %s %s"
+                               % (self.num_edge, tuple(edge_weight.shape), edge_weight.dtype))
+        if edge_weight.device != self.device:
+            raise RuntimeError("bind_weight: edge_weight is on %s, the plan on %s" % (edge_weight.device, self.device))
+        key = (edge_weight.data_ptr(), _version(edge_weight), edge_weight.dtype, tuple(edge_weight.shape),
                edge_weight.stride())
         if key == self._weight_key:
             return
         ew = edge_weight.detach().contiguous()
-        rc = _capi.lib().ultra_rspmm_set_edge_weight(self._handle, ew.data_ptr(), _DTYPE_ID[ew.dtype],
-                                                     _stream_ptr(self.device))
+        with torch.cuda.device(self.device):  # the permute kernel must launch on the plan's device, not the current one
+            rc = _capi.lib().ultra_rspmm_set_edge_weight(self._handle, ew.data_ptr(), _DTYPE_ID[ew.dtype],
+                                                         _stream_ptr(self.device))
         _capi.check(rc, "ultra_rspmm_set_edge_weight")
         self._weight_key = key
         self._weight_ref = edge_weight  # keep the storage alive so the key cannot be recycled
@@ -87,10 +127,17 @@ class GraphPlan:
 
 
 class PlanCache:
-    """LRU of GraphPlans keyed on tensor identity + version (holds the tensors so addresses are not recycled)."""
+    """LRU of GraphPlans keyed on tensor identity + version (holds the tensors so addresses are not recycled).
 
-    def __init__(self, capacity=16):
+    Bounded by entries AND by device bytes: a caller that hands a fresh edge tensor to every call (the reference's
+    training loop after remove_easy_edges, /root/reference/ultra/base_nbfnet.py:54-77) misses every time, and each
+    stale plan pins its workspace; the byte budget (default 1 GiB, ULTRA_PLAN_CACHE_MB) evicts them early.  Cache hits
+    need stable edge tensors - keep `edge_index` / `edge_type` objects alive across layers and steps."""
+
+    def __init__(self, capacity=8, max_bytes=None):
+        import os
         self.capacity = capacity
+        self.max_bytes = int(os.environ.get("ULTRA_PLAN_CACHE_MB", "1024")) << 20 if max_bytes is None else max_bytes
         self._entries = collections.OrderedDict()
         self._lock = threading.Lock()
         self.hits = 0
@@ -98,8 +145,8 @@ class PlanCache:
 
     @staticmethod
     def _key(edge_index, edge_type, num_node, num_relation):
-        return (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), edge_index.stride(),
-                edge_type.data_ptr(), edge_type._version, tuple(edge_type.shape), edge_type.stride(),
+        return (edge_index.data_ptr(), _version(edge_index), tuple(edge_index.shape), edge_index.stride(),
+                edge_type.data_ptr(), _version(edge_type), tuple(edge_type.shape), edge_type.stride(),
                 str(edge_index.device), int(num_node), int(num_relation))
 
     def get(self, edge_index, edge_type, num_node, num_relation, device=None):
@@ -118,7 +165,8 @@ class PlanCache:
         with self._lock:
             self.misses += 1
             self._entries[key] = (plan, edge_index, edge_type)
-            while len(self._entries) > self.capacity:
+            while len(self._entries) > 1 and (len(self._entries) > self.capacity or
+                                              sum(e[0].nbytes() for e in self._entries.values()) > self.max_bytes):
                 self._entries.popitem(last=False)
         return plan
 

@@ -22,7 +22,7 @@ import torch
 from torch import autograd
 
 from .. import _capi
-from ..plan import plan_cache, _DTYPE_ID, _stream_ptr
+from ..plan import plan_cache, _DTYPE_ID, _stream_ptr, _version
 
 module = sys.modules[__name__]
 
@@ -89,7 +89,7 @@ def _get_plan(edge_index, edge_type, num_node, num_relation):
 
 def _bind_host_weight(plan, edge_weight, device):
     """Host-resident weights: upload once per (tensor, version); the device copy is kept on the plan."""
-    key = (edge_weight.data_ptr(), edge_weight._version, edge_weight.dtype, tuple(edge_weight.shape))
+    key = (edge_weight.data_ptr(), _version(edge_weight), edge_weight.dtype, tuple(edge_weight.shape))
     if getattr(plan, "_host_weight_key", None) != key:
         plan._host_weight_dev = edge_weight.detach().to(device)
         plan._host_weight_key = key

@@ -60,11 +60,13 @@ class OverlappedStateGather:
         states = g.wait()                                                # list of (B, N, d) tensors, one per layer
     """
 
-    def __init__(self, batch_size, group=None, layers=None, reserve_sms=8):
+    def __init__(self, batch_size, group=None, layers=None, reserve_sms=8, plan=None):
         """reserve_sms: SMs left free for NCCL while gathers are in flight (the rspmm / update kernels are persistent
-        and otherwise fill every SM, which would serialise the collective behind them); restored by wait()."""
+        and otherwise fill every SM, which would serialise the collective behind them).  The reservation is a field of
+        the GraphPlan the layers run on (`plan`, per plan, no process-global state); restored by wait()."""
         self.batch_size = batch_size
         self.reserve_sms = reserve_sms
+        self.plan = plan
         self._limited = False
         self.group = group
         self.layers = None if layers is None else set(layers)  # which layer indices to gather (None = every layer)
@@ -76,10 +78,9 @@ class OverlappedStateGather:
         if self.layers is not None and layer_idx not in self.layers:
             return
         if hidden.is_cuda:
-            if self.reserve_sms and not self._limited:
-                from . import _capi
-                sms = torch.cuda.get_device_properties(hidden.device).multi_processor_count
-                _capi.set_tunable("sm_limit", max(sms - self.reserve_sms, 1))
+            if self.reserve_sms and self.plan is not None and not self._limited:
+                sms = self.plan.info(7)
+                self.plan.set_sm_limit(max(sms - self.reserve_sms, 1))
                 self._limited = True
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=hidden.device)
@@ -99,11 +100,12 @@ class OverlappedStateGather:
     def wait(self):
         for out, done in self._pending:
             if done is not None:
-                torch.cuda.current_stream(out.device).wait_event(done)
+                cur = torch.cuda.current_stream(out.device)
+                cur.wait_event(done)
+                out.record_stream(cur)  # allocated on the side stream, consumed on this one
             self.results.append(out)
         self._pending = []
         if self._limited:
-            from . import _capi
-            _capi.set_tunable("sm_limit", 0)
+            self.plan.set_sm_limit(0)
             self._limited = False
         return self.results
