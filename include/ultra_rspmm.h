@@ -155,16 +155,20 @@ int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype,
  * directly - relation (B, R, d), input/output/output_grad/input_grad (B, N, d), relation_grad (B, R, d) - and can
  * fold the layer's boundary term (the self-loop message, layers.py:199-207) into the store:
  *     output = Nary(rspmm(...), boundary)    i.e. + for sum, max / min for max / min;   boundary may be NULL.
+ * relation_broadcast != 0: `relation` is ONE (R, d) block shared by every head - the relation-graph stack expands a
+ * single nn.Embedding over the batch (/root/reference/ultra/layers.py:76); the kernels read it with head stride 0 instead
+ * of a materialised (B, R, d) copy.  relation_grad is still written per head, (B, R, d): the caller sums it over B.
  * Requirements: head_dim * sizeof(dtype) is a multiple of 128 bytes, pointers 16-byte aligned.  For min/max the
  * `output` handed to backward_heads is the (boundary-folded) forward output.  weight_grad is not offered here.
  */
 int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
                               const void *input, const void *boundary, void *output, int64_t num_heads,
-                              int64_t head_dim, void *scratch, size_t scratch_bytes, void *stream);
+                              int64_t head_dim, int relation_broadcast, void *scratch, size_t scratch_bytes,
+                              void *stream);
 int ultra_rspmm_backward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
                                const void *input, const void *output, const void *output_grad, void *relation_grad,
-                               void *input_grad, int64_t num_heads, int64_t head_dim, void *scratch,
-                               size_t scratch_bytes, void *stream);
+                               void *input_grad, int64_t num_heads, int64_t head_dim, int relation_broadcast,
+                               void *scratch, size_t scratch_bytes, void *stream);
 
 /*
  * End-to-end forward from HOST buffers (pinned for full speed): relation/input/output live in host memory;
@@ -194,6 +198,17 @@ int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_
                             const float *ln_gamma, const float *ln_beta, float *out, int64_t num_rows, int64_t in_dim,
                             int64_t out_dim, float ln_eps, int layer_norm, int relu, int shortcut, int sm_limit,
                             void *stream);
+
+/*
+ * All per-layer relation projections of the entity stack in ONE launch, fp32:
+ *     out[l, m, :] = W2[l] . relu( W1[l] . x[m, :] + b1[l] ) + b2[l]          l < num_layers, m < num_rows
+ * replaces the nn.Sequential(Linear(64,64), ReLU, Linear(64,64)) every entity layer applies to the SAME (B, R, 64)
+ * relation representations (/root/reference/ultra/layers.py:60-64,80): 3 launches x 6 layers in the reference.
+ *   x (num_rows, 64);  w1_t, w2_t (num_layers, 64, 64) = the nn.Linear weights TRANSPOSED ([k][n]);  b1, b2 (num_layers, 64)
+ *   out (num_layers, num_rows, 64).  Only dim == 64; other sizes return an error and the caller keeps its own MLP.
+ */
+int ultra_relation_project_f32(const float *x, const float *w1_t, const float *b1, const float *w2_t, const float *b2,
+                               float *out, int64_t num_rows, int64_t dim, int64_t num_layers, void *stream);
 
 #ifdef __cplusplus
 }

@@ -264,3 +264,110 @@ def test_ultra_forward_with_checkpoint_weights_matches_reference_fixture(cuda_de
         tol = 1e-4  # 12 layers of fp32 Linear/LayerNorm end to end; rspmm itself is held to 1e-5 elsewhere
         torch.testing.assert_close(got.cpu(), exp, rtol=tol, atol=tol * float(exp.abs().max()),
                                    msg=lambda m: name + ": " + m)
+
+
+# ---- round 2: shared relation block, one-launch projections, the full-stack runner ---------------
+@pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "add"), ("min", "mul")])
+def test_rspmm_heads_broadcast_relation_equals_expanded(cuda_device, sum, mul):
+    """relation (R, d) read with head stride 0 must be BIT-identical to the materialised (B, R, d) expand
+    (layers.py:76), forward and input_grad; relation_grad == the expand's autograd sum over heads (fp32 sum order
+    differs: per-head grads are summed by torch in both cases, so this is bit-identical as well)."""
+    from ultra_b200.fused import rspmm_heads
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    B, N, R, d, E = 6, 300, 4, 64, 9000
+    ei = torch.randint(0, N, (2, E), generator=g).to(dev)
+    et = torch.randint(0, R, (E,), generator=g).to(dev)
+    w = torch.ones(E, device=dev)
+    emb = torch.randn(R, d, generator=g)
+    x = torch.randn(B, N, d, generator=g)
+    bd = torch.randn(B, N, d, generator=g)
+    og = torch.randn(B, N, d, generator=g).to(dev)
+    e1, x1 = emb.to(dev).requires_grad_(), x.to(dev).requires_grad_()
+    out1 = rspmm_heads(ei, et, w, e1, x1, bd.to(dev), sum=sum, mul=mul)
+    out1.backward(og)
+    e2, x2 = emb.to(dev).requires_grad_(), x.to(dev).requires_grad_()
+    out2 = rspmm_heads(ei, et, w, e2.expand(B, -1, -1).contiguous(), x2, bd.to(dev), sum=sum, mul=mul)
+    out2.backward(og)
+    assert torch.equal(out1, out2)
+    assert torch.equal(x1.grad, x2.grad)
+    torch.testing.assert_close(e1.grad, e2.grad, rtol=1e-6, atol=1e-6 * float(e2.grad.abs().max()))
+
+
+@pytest.mark.parametrize("rows", [1, 63, 64, 474 * 7, 474 * 128])
+def test_relation_project_kernel(cuda_device, rows):
+    """All six relation_projection MLPs in one launch == the six nn.Sequential modules (layers.py:60-64,80)."""
+    from ultra_b200 import fused
+    dev = cuda_device
+    torch.manual_seed(12)
+    projs = [torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64)).to(dev)
+             for _ in range(6)]
+    x = torch.randn(rows, 64, device=dev) * 2
+    with torch.no_grad():
+        assert fused.relation_project_ok(x, projs)
+        got = fused.relation_project(x, projs)
+        assert got.shape == (6, rows, 64)
+        for l, p in enumerate(projs):
+            exp = p(x.double().float()) if False else torch.nn.functional.linear(
+                torch.relu(torch.nn.functional.linear(x.double(), p[0].weight.double(), p[0].bias.double())),
+                p[2].weight.double(), p[2].bias.double())
+            torch.testing.assert_close(got[l].double(), exp, rtol=1e-5, atol=1e-5 * float(exp.abs().max()))
+
+
+@pytest.mark.parametrize("graphed", [False, True], ids=["eager", "cuda_graph"])
+def test_ultra_nbfnet_runner_with_checkpoint_weights(cuda_device, graphed):
+    """ultra_b200.nbfnet.UltraNBFNet on the GPU fast path (shared relation block, one-launch projections, head-major
+    kernels, tcgen05 epilogue, split-weight scoring; optionally captured as ONE CUDA graph) against the reference
+    fixture computed with the unmodified reference CPU rspmm and the shipped ultra_3g weights."""
+    from oracle import layer_ref
+    from helpers import load_layer_golden
+    from ultra_b200.nbfnet import UltraNBFNet, CudaGraphRunner
+    dev = cuda_device
+    fx = load_layer_golden()
+    model = UltraNBFNet().to(dev).eval()
+    model.load_state_dict(layer_ref.state_dict_from_npz(fx), strict=True)
+    t = lambda k: torch.from_numpy(fx[k]).to(dev)  # noqa: E731
+    rel_graph = (t("rel_edge_index"), t("rel_edge_type"), int(fx["num_relation"]))
+    graph = (t("edge_index"), t("edge_type"), int(fx["num_node"]))
+    fn = lambda h, r: model(rel_graph, graph, h, r)  # noqa: E731  all-tail scores (B, N)
+    with torch.no_grad():
+        if graphed:
+            runner = CudaGraphRunner(fn, t("h_index"), t("r_index"))
+            # replay with permuted-then-restored inputs: the static buffers must really feed the graph
+            perm = torch.tensor([1, 0, 3, 2], device=dev)
+            swapped = runner(t("h_index")[perm], t("r_index")[perm]).clone()
+            scores = runner(t("h_index"), t("r_index")).clone()
+            assert torch.equal(swapped[perm], scores)
+        else:
+            scores = fn(t("h_index"), t("r_index"))
+        rel = model.relation_representations(*rel_graph, t("r_index"))
+    tol = 1e-4
+    exp = torch.from_numpy(fx["relation_representations"])
+    torch.testing.assert_close(rel.cpu(), exp, rtol=tol, atol=tol * float(exp.abs().max()))
+    exp = torch.from_numpy(fx["score"])
+    got = scores.gather(1, t("t_index")).cpu()
+    torch.testing.assert_close(got, exp, rtol=tol, atol=tol * float(exp.abs().max()))
+
+
+def test_bind_weight_on_non_current_device_is_guarded(cuda_device):
+    """plans must launch on THEIR device even when another device is current (needs >= 2 GPUs to bite; with one
+    GPU it still checks that a plan built under a device guard works from outside it)."""
+    from ultra_b200.rspmm import generalized_rspmm
+    from helpers import random_case, oracle_all, assert_close_ref
+    target = torch.device("cuda", torch.cuda.device_count() - 1)
+    ei, et, w, rel, x, _ = random_case(71, 200, 3000, 5, 64)
+    with torch.cuda.device(0):
+        out = generalized_rspmm(ei.to(target), et.to(target), w.to(target), rel.to(target), x.to(target))
+    assert_close_ref(out, oracle_all("add", "mul", ei, et, w, rel, x), "non-current device")
+
+
+def test_inference_mode_tensors_are_accepted(cuda_device):
+    """inference tensors have no version counter; the plan / weight cache keys must not read it."""
+    from ultra_b200.rspmm import generalized_rspmm
+    from helpers import random_case, oracle_all, assert_close_ref
+    ei, et, w, rel, x, _ = random_case(72, 150, 2000, 4, 64)
+    d = cuda_device
+    with torch.inference_mode():
+        ones = torch.ones(ei.shape[1], device=d)  # created inside the mode: an inference tensor
+        out = generalized_rspmm(ei.to(d), et.to(d), ones, rel.to(d), x.to(d))
+    assert_close_ref(out, oracle_all("add", "mul", ei, et, torch.ones(ei.shape[1]), rel, x), "inference mode")

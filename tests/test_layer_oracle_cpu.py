@@ -85,3 +85,32 @@ def test_relation_graph_restatements_agree(fx):
     assert (num_rel_rel, num_rel_node) == (4, int(fx["num_relation"]))
     assert torch.equal(ei, torch.from_numpy(fx["rel_edge_index"]))
     assert torch.equal(et, torch.from_numpy(fx["rel_edge_type"]))
+
+
+def test_ultra_nbfnet_runner_matches_fixture(fx, monkeypatch):
+    """ultra_b200.nbfnet.UltraNBFNet (the full-stack runner the C3 bench / head-shard scaling use) loads the checkpoint
+    with strict=True under the reference's key names and, with rspmm replaced by the oracle, reproduces the fixture -
+    including score_all's split-weight scoring (no (B, N, 128) concatenation) against the gathered-tail scores."""
+    import ultra_b200.layer as product_layer
+    from ultra_b200.nbfnet import UltraNBFNet
+
+    def oracle_rspmm(edge_index, edge_type, edge_weight, relation, input, sum="add", mul="mul"):
+        sei, stt, sw, _ = oracle.sort_edges(edge_index.numpy(), edge_type.numpy(), edge_weight.numpy())
+        return torch.from_numpy(oracle.c_forward(sum, mul, sei, stt, sw, relation.contiguous().numpy(),
+                                                 input.contiguous().numpy()))
+
+    monkeypatch.setattr(product_layer, "generalized_rspmm", oracle_rspmm)
+    monkeypatch.setattr(product_layer.GeneralizedRelationalConv, "fuse", False)
+    model = UltraNBFNet().eval()
+    model.load_state_dict(layer_ref.state_dict_from_npz(fx), strict=True)
+    t = lambda k: torch.from_numpy(np.asarray(fx[k]))  # noqa: E731
+    rel_graph = (t("rel_edge_index"), t("rel_edge_type"), int(fx["num_relation"]))
+    graph = (t("edge_index"), t("edge_type"), int(fx["num_node"]))
+    with torch.no_grad():
+        rel = model.relation_representations(*rel_graph, t("r_index"))
+        close(rel, fx["relation_representations"], "relation representations")
+        score = model(rel_graph, graph, t("h_index"), t("r_index"), t("t_index"))
+        close(score, fx["score"], "scores", tol=5e-5)
+        all_scores = model(rel_graph, graph, t("h_index"), t("r_index"))  # every entity as the tail
+        assert all_scores.shape == (4, int(fx["num_node"]))
+        close(all_scores.gather(1, t("t_index")), fx["score"], "score_all at the fixture's tails", tol=5e-5)

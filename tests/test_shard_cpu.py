@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ultra_b200.shard import head_range, shard_heads, all_gather_heads, OverlappedStateGather
+from ultra_b200.shard import head_range, shard_heads, all_gather_heads, OverlappedStateGather, ShardedUltra
 
 
 def test_head_range_partitions_exactly():
@@ -67,7 +67,11 @@ def _check(rank, world, batch, out_q):
             og_last.after_layer(li, h)
         last = og_last.wait()
         ok3 = len(last) == 1 and torch.equal(last[0], ref)
-        out_q.put((rank, batch, bool(ok1), bool(ok2), bool(ok3)))
+        # ShardedUltra: local heads -> scores -> ONE all-gather of the (B_local, N) score rows == the unsharded scores
+        model = lambda rg, gr, hh, rr: (hh.float() * 3 + rr.float()).unsqueeze(1) + torch.arange(6).float()  # noqa: E731
+        h_index, r_index = torch.arange(batch) % 5, (torch.arange(batch) * 7) % 3
+        ok4 = torch.equal(ShardedUltra(model)(None, None, h_index, r_index), model(None, None, h_index, r_index))
+        out_q.put((rank, batch, bool(ok1), bool(ok2), bool(ok3 and ok4)))
 
 
 def test_all_gather_heads_gloo_world2():

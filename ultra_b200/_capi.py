@@ -30,9 +30,10 @@ SYMBOLS = {
     "ultra_rspmm_forward": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_backward": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_forward_pna": (_int, [_vp, _int, _int, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
-    "ultra_rspmm_forward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
-    "ultra_rspmm_backward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz,
-                                          _vp]),
+    "ultra_rspmm_forward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
+    "ultra_rspmm_backward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp,
+                                          _sz, _vp]),
+    "ultra_relation_project_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "ultra_nbfnet_update_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float, _int, _int,
                                        _int, _int, _vp]),
     "ultra_rspmm_host_staging_bytes": (_sz, [_vp, _i64, _i64, _int]),

@@ -46,7 +46,7 @@ template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *>
 template <typename T, int MODE, int SUM, int MUL>
 int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input, const T *output,
                 const T *outgrad, T *dst, T *scratch, int64_t D, cudaStream_t stream, int64_t heads = 0,
-                const T *boundary = nullptr, T *rgrad = nullptr) {
+                const T *boundary = nullptr, T *rgrad = nullptr, bool rel_broadcast = false) {
     using Nd = Needs<MODE, SUM, MUL>;
     constexpr int ORD = order_of(MODE);  // BWD_BOTH walks the by-column order
     const SegOrder &so = plan->ord[ORD];
@@ -68,15 +68,17 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         lay.group_cols = (int)d;
         lay.row_bytes = (unsigned)(d * sizeof(T));
         lay.grp_node_bytes = (long long)plan->N * lay.row_bytes;
-        lay.grp_rel_bytes = (long long)plan->R * lay.row_bytes;
+        lay.grp_rgrad_bytes = (long long)plan->R * lay.row_bytes;
+        lay.grp_rel_bytes = rel_broadcast ? 0 : lay.grp_rgrad_bytes;
     } else {
         lay.tpg = (int)((D + TILE - 1) / TILE);
         lay.group_cols = (int)D;
         lay.row_bytes = (unsigned)(D * sizeof(T));
         lay.grp_node_bytes = 0;
         lay.grp_rel_bytes = 0;
+        lay.grp_rgrad_bytes = 0;
     }
-    const long long dst_grp_bytes = MODE == BWD_REL ? lay.grp_rel_bytes : lay.grp_node_bytes;
+    const long long dst_grp_bytes = MODE == BWD_REL ? lay.grp_rgrad_bytes : lay.grp_node_bytes;
 
     if (heads == 0 && !vec_ok<T>(D, {relation, input, output, outgrad, dst, scratch, boundary, rgrad})) {
         if constexpr (MODE == BWD_BOTH) { set_error("fused backward needs the vector path"); return 1; } else {
@@ -182,15 +184,16 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
 
 template <typename T, int SUM, int MUL>
 int forward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, void *output, int64_t D,
-              void *scratch, cudaStream_t stream, int64_t heads = 0, const void *boundary = nullptr) {
+              void *scratch, cudaStream_t stream, int64_t heads = 0, const void *boundary = nullptr,
+              bool rel_broadcast = false) {
     return launch_pass<T, FWD, SUM, MUL>(plan, (const T *)relation, (const T *)input, nullptr, nullptr, (T *)output,
-                                         (T *)scratch, D, stream, heads, (const T *)boundary);
+                                         (T *)scratch, D, stream, heads, (const T *)boundary, nullptr, rel_broadcast);
 }
 
 template <typename T, int SUM, int MUL>
 int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *input, const void *output,
                const void *outgrad, void *wgrad, void *rgrad, void *igrad, int64_t D, void *scratch,
-               cudaStream_t stream, int64_t heads = 0) {
+               cudaStream_t stream, int64_t heads = 0, bool rel_broadcast = false) {
     int rc;
     const bool fused = g_bwd_fused_relgrad.load() != 0 && plan->R > 0 &&
                        (heads > 0 || vec_ok<T>(D, {relation, input, output, outgrad, igrad, rgrad, scratch}));
@@ -199,14 +202,16 @@ int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *i
         CUDA_TRY(cudaMemsetAsync(rgrad, 0, (size_t)plan->R * (size_t)D * sizeof(T), stream));
         rc = launch_pass<T, BWD_BOTH, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
                                                 (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads,
-                                                nullptr, (T *)rgrad);
+                                                nullptr, (T *)rgrad, rel_broadcast);
         if (rc) return rc;
     } else {
         rc = launch_pass<T, BWD_IN, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
-                                              (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads);
+                                              (const T *)outgrad, (T *)igrad, (T *)scratch, D, stream, heads, nullptr,
+                                              nullptr, rel_broadcast);
         if (rc) return rc;
         rc = launch_pass<T, BWD_REL, SUM, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output,
-                                               (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream, heads);
+                                               (const T *)outgrad, (T *)rgrad, (T *)scratch, D, stream, heads, nullptr,
+                                               nullptr, rel_broadcast);
         if (rc) return rc;
     }
     if (wgrad != nullptr && heads > 0) { set_error("weight_grad is not available in the head-major layout"); return 1; }
@@ -403,24 +408,27 @@ int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype,
 
 int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
                               const void *input, const void *boundary, void *output, int64_t num_heads,
-                              int64_t head_dim, void *scratch, size_t scratch_bytes_, void *stream_) {
+                              int64_t head_dim, int relation_broadcast, void *scratch, size_t scratch_bytes_,
+                              void *stream_) {
     if (num_heads <= 0 || head_dim <= 0) { set_error("forward_heads: num_heads / head_dim must be positive"); return 1; }
     const int64_t dim = num_heads * head_dim;
     if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
     if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("forward_heads: scratch too small"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (dtype == ULTRA_RSPMM_F32) {
-        DISPATCH_OPS(forward_t, float, plan, relation, input, output, dim, scratch, stream, num_heads, boundary)
+        DISPATCH_OPS(forward_t, float, plan, relation, input, output, dim, scratch, stream, num_heads, boundary,
+                     relation_broadcast != 0)
     } else {
-        DISPATCH_OPS(forward_t, double, plan, relation, input, output, dim, scratch, stream, num_heads, boundary)
+        DISPATCH_OPS(forward_t, double, plan, relation, input, output, dim, scratch, stream, num_heads, boundary,
+                     relation_broadcast != 0)
     }
     return 1;
 }
 
 int ultra_rspmm_backward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,
                                const void *input, const void *output, const void *output_grad, void *relation_grad,
-                               void *input_grad, int64_t num_heads, int64_t head_dim, void *scratch,
-                               size_t scratch_bytes_, void *stream_) {
+                               void *input_grad, int64_t num_heads, int64_t head_dim, int relation_broadcast,
+                               void *scratch, size_t scratch_bytes_, void *stream_) {
     if (num_heads <= 0 || head_dim <= 0) { set_error("backward_heads: num_heads / head_dim must be positive"); return 1; }
     const int64_t dim = num_heads * head_dim;
     if (int rc = check_common(plan, sum_op, mul_op, dtype, dim)) return rc;
@@ -428,10 +436,10 @@ int ultra_rspmm_backward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (dtype == ULTRA_RSPMM_F32) {
         DISPATCH_OPS(backward_t, float, plan, relation, input, output, output_grad, nullptr, relation_grad, input_grad,
-                     dim, scratch, stream, num_heads)
+                     dim, scratch, stream, num_heads, relation_broadcast != 0)
     } else {
         DISPATCH_OPS(backward_t, double, plan, relation, input, output, output_grad, nullptr, relation_grad,
-                     input_grad, dim, scratch, stream, num_heads)
+                     input_grad, dim, scratch, stream, num_heads, relation_broadcast != 0)
     }
     return 1;
 }

@@ -154,7 +154,9 @@ struct Layout {
     int group_cols;              // columns per group (D flat, d heads) - ragged last tile check
     unsigned row_bytes;
     long long grp_node_bytes;    // group stride of the N-row matrices (input, output, outgrad, boundary, input_grad)
-    long long grp_rel_bytes;     // group stride of the R-row matrices (relation, relation_grad)
+    long long grp_rel_bytes;     // group stride of the relation matrix; 0 = ONE (R, d) block broadcast over the heads (the
+                                 // relation-graph stack expands a single embedding, ultra/layers.py:76 - never materialised)
+    long long grp_rgrad_bytes;   // group stride of relation_grad (always per head; the caller sums a broadcast one)
 };
 
 template <typename T> struct SegParams {
@@ -238,6 +240,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const unsigned row_bytes = p.lay.row_bytes;
     const size_t off_n = (size_t)grp * p.lay.grp_node_bytes + (size_t)cin * sizeof(T);
     const size_t off_r = (size_t)grp * p.lay.grp_rel_bytes + (size_t)cin * sizeof(T);
+    const size_t off_rg = (size_t)grp * p.lay.grp_rgrad_bytes + (size_t)cin * sizeof(T);
 
     const int4 it = __ldg(p.items + (size_t)wi * kSubPerWarp + sg);
     const int e0 = it.x, slot = it.w;
@@ -256,8 +259,8 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const char *in_c = reinterpret_cast<const char *>(p.input) + off_n;
     const char *rel_c = reinterpret_cast<const char *>(p.relation) + off_r;
     const char *self_c = by_col(MODE) ? in_c : rel_c;
-    char *dst_c = reinterpret_cast<char *>(p.dst) + (MODE == BWD_REL ? off_r : off_n);
-    char *rg_c = reinterpret_cast<char *>(p.rgrad) + off_r;
+    char *dst_c = reinterpret_cast<char *>(p.dst) + (MODE == BWD_REL ? off_rg : off_n);
+    char *rg_c = reinterpret_cast<char *>(p.rgrad) + off_rg;
     const char *bnd_c = reinterpret_cast<const char *>(p.boundary) + off_n;
     const bool has_bnd = (MODE == FWD) && p.boundary != nullptr;
     uint32_t rel_q = rel_s_addr + (uint32_t)q * 16u;

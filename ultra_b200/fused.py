@@ -27,9 +27,12 @@ class _RSPMMHeadsFunction(autograd.Function):
         lib = _capi.lib()
         sum_id, mul_id = _capi.SUM_IDS[sum], _capi.MUL_IDS[mul]
         B, N, d = input.shape
-        R = relation.shape[1]
-        if relation.shape[0] != B or relation.shape[2] != d:
-            raise RuntimeError("rspmm_heads: relation must be (B, R, d) matching input (B, N, d)")
+        # relation (B, R, d), or (R, d): ONE block shared by every head (the relation-graph stack, layers.py:76) that
+        # the kernels read with head stride 0 - the (B, R, d) expand is never materialised
+        broadcast = relation.dim() == 2
+        R = relation.shape[-2]
+        if relation.shape[-1] != d or (not broadcast and (relation.dim() != 3 or relation.shape[0] != B)):
+            raise RuntimeError("rspmm_heads: relation must be (B, R, d) or (R, d) matching input (B, N, d)")
         if boundary is not None and boundary.shape != input.shape:
             raise RuntimeError("rspmm_heads: boundary must have the shape of input")
         if relation.dtype != input.dtype or edge_weight.dtype != input.dtype or \
@@ -49,10 +52,10 @@ class _RSPMMHeadsFunction(autograd.Function):
         with torch.cuda.device(input.device):
             rc = lib.ultra_rspmm_forward_heads(plan.handle, sum_id, mul_id, _DTYPE_ID[input.dtype], rel_c.data_ptr(),
                                                in_c.data_ptr(), None if bnd_c is None else bnd_c.data_ptr(),
-                                               output.data_ptr(), B, d, scratch.data_ptr(), scratch.numel(),
-                                               _stream_ptr(input.device))
+                                               output.data_ptr(), B, d, 1 if broadcast else 0, scratch.data_ptr(),
+                                               scratch.numel(), _stream_ptr(input.device))
         _capi.check(rc, "ultra_rspmm_forward_heads")
-        ctx.plan, ctx.ids, ctx.sum = plan, (sum_id, mul_id), sum
+        ctx.plan, ctx.ids, ctx.sum, ctx.broadcast = plan, (sum_id, mul_id), sum, broadcast
         ctx.has_boundary = boundary is not None
         ctx.save_for_backward(edge_weight, rel_c, in_c, output, bnd_c if bnd_c is not None else torch.empty(0))
         return output
@@ -67,14 +70,18 @@ class _RSPMMHeadsFunction(autograd.Function):
         plan.bind_weight(edge_weight)
         B, N, d = in_c.shape
         og = output_grad.contiguous()
-        relation_grad, input_grad = torch.empty_like(rel_c), torch.empty_like(in_c)
+        relation_grad = in_c.new_empty((B,) + tuple(rel_c.shape[-2:]))
+        input_grad = torch.empty_like(in_c)
         scratch = plan.scratch(B * d, in_c.dtype)
         with torch.cuda.device(in_c.device):
             rc = lib.ultra_rspmm_backward_heads(plan.handle, ctx.ids[0], ctx.ids[1], _DTYPE_ID[in_c.dtype],
                                                 rel_c.data_ptr(), in_c.data_ptr(), output.data_ptr(), og.data_ptr(),
                                                 relation_grad.data_ptr(), input_grad.data_ptr(), B, d,
-                                                scratch.data_ptr(), scratch.numel(), _stream_ptr(in_c.device))
+                                                1 if ctx.broadcast else 0, scratch.data_ptr(), scratch.numel(),
+                                                _stream_ptr(in_c.device))
         _capi.check(rc, "ultra_rspmm_backward_heads")
+        if ctx.broadcast:  # d/d(shared embedding) = sum over the heads that read it (what autograd does for expand)
+            relation_grad = relation_grad.sum(0)
         boundary_grad = None
         if ctx.has_boundary and ctx.needs_input_grad[5]:
             # out = Nary(agg, boundary): d out / d boundary = 1 (sum) or [out == boundary] (min / max, operator.cuh:62,75)
@@ -89,6 +96,39 @@ def rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary=No
     if not heads_layout_ok(input):
         raise RuntimeError("rspmm_heads needs CUDA fp32/fp64 (B, N, d) input with d * itemsize % 128 == 0")
     return _RSPMMHeadsFunction.apply(edge_index, edge_type, edge_weight, relation, input, boundary, sum, mul)
+
+
+def relation_project_ok(rel_repr, projections):
+    """All `projections` are Sequential(Linear(64,64), ReLU, Linear(64,64)) on fp32 CUDA (B, R, 64); inference only."""
+    if not (rel_repr.is_cuda and rel_repr.dtype == torch.float32 and rel_repr.shape[-1] == 64
+            and not torch.is_grad_enabled()):
+        return False
+    for p in projections:
+        if not (len(p) == 3 and isinstance(p[0], torch.nn.Linear) and isinstance(p[1], torch.nn.ReLU)
+                and isinstance(p[2], torch.nn.Linear) and p[0].weight.shape == (64, 64) and p[2].weight.shape == (64, 64)
+                and p[0].bias is not None and p[2].bias is not None and p[0].weight.dtype == torch.float32):
+            return False
+    return True
+
+
+def relation_project(rel_repr, projections):
+    """Every layer's relation_projection MLP of the same (B, R, 64) relation representations in ONE launch
+    (layers.py:60-64,80).  Returns (L, B, R, 64)."""
+    lib = _capi.lib()
+    x = rel_repr.contiguous()
+    L = len(projections)
+    with torch.no_grad():
+        w1 = torch.stack([p[0].weight.t() for p in projections]).contiguous()   # (L, 64, 64) [k][n]
+        b1 = torch.stack([p[0].bias for p in projections]).contiguous()
+        w2 = torch.stack([p[2].weight.t() for p in projections]).contiguous()
+        b2 = torch.stack([p[2].bias for p in projections]).contiguous()
+    out = x.new_empty((L,) + tuple(x.shape))
+    rows = x.numel() // 64
+    with torch.cuda.device(x.device):
+        rc = lib.ultra_relation_project_f32(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                            out.data_ptr(), rows, 64, L, _stream_ptr(x.device))
+    _capi.check(rc, "ultra_relation_project_f32")
+    return out
 
 
 def nbfnet_update_ok(x, u, linear, activation):

@@ -41,15 +41,21 @@ class GeneralizedRelationalConv(nn.Module):
 
     fuse = True  # class-wide switch for the head-major / fused-epilogue fast path (set False to force the restatement)
 
-    def forward(self, input, query, boundary, edge_index, edge_type, size, edge_weight=None, shortcut=False):
+    def forward(self, input, query, boundary, edge_index, edge_type, size, edge_weight=None, shortcut=False,
+                relation=None):
         """input, boundary: (B, N, d); query: (B, d_q); returns (B, N, output_dim).  layers.py:67-88.
         `shortcut=True` (not in the reference signature) also adds `input` to the result, i.e. the residual of the
-        Bellman-Ford loop (models.py:158-160), so that it can be folded into the fused epilogue."""
+        Bellman-Ford loop (models.py:158-160), so that it can be folded into the fused epilogue.
+        `relation` (not in the reference signature): this layer's already-projected (B, R, d) relation, when the caller
+        projected all layers at once (ultra_b200.nbfnet); None = compute it here like the reference."""
         batch_size = len(query)
-        if self.dependent:
+        shared = False  # relation is ONE (R, d) block for every head (embedding mode, layers.py:76)
+        if relation is not None:
+            pass
+        elif self.dependent:
             relation = self.relation_linear(query).view(batch_size, self.num_relation, self.input_dim)
         elif not self.project_relations:
-            relation = self.relation.weight.expand(batch_size, -1, -1)
+            relation, shared = self.relation.weight, True
         else:
             relation = self.relation_projection(self.relation)
         if edge_weight is None:
@@ -67,6 +73,8 @@ class GeneralizedRelationalConv(nn.Module):
                 return fused.nbfnet_update(input, update, self.linear, self.layer_norm,
                                            relu=self.activation is not None, shortcut=shortcut, sm_limit=plan.sm_limit)
         else:
+            if shared:
+                relation = relation.expand(batch_size, -1, -1)
             update = self.message_and_aggregate(edge_index, input, relation, boundary, edge_type, edge_weight, size[0])
         output = self.update(update, input)
         return output + input if shortcut else output
@@ -75,7 +83,8 @@ class GeneralizedRelationalConv(nn.Module):
         """Same result as message_and_aggregate for sum / mean / max, but the (B, N, d) state is consumed and produced
         in place by the head-major kernels: no transpose copies, boundary folded into the store."""
         mul = self.message2mul[self.message_func]
-        relation = relation.contiguous()  # materialises the (B, R, d) expand of the embedding mode (tiny)
+        # relation is (B, R, d), or the (R, d) embedding itself in the relation-graph stack: rspmm_heads reads that one
+        # block for every head (head stride 0), the reference's expand (layers.py:76) is never materialised
         if self.aggregate_func == "max":
             return fused.rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary, sum="max", mul=mul)
         update = fused.rspmm_heads(edge_index, edge_type, edge_weight, relation, input, boundary, sum="add", mul=mul)

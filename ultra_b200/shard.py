@@ -109,3 +109,33 @@ class OverlappedStateGather:
             self.plan.set_sm_limit(0)
             self._limited = False
         return self.results
+
+
+class ShardedUltra:
+    """Head-sharded Ultra forward: rank g of G owns the queries (heads) [g*B/G, (g+1)*B/G) of the batch.
+
+    Heads ARE the batch samples (one (h, r) query each), so this is the reference's own scaling axis - batch-sharded DDP
+    (/root/reference/script/run.py:33,45) - inside one process group: both NBFNet stacks and the scoring MLP run on local
+    heads with no communication, and ONE all-gather of the (B_local, N) score rows gives every rank what the caller of
+    `Ultra.forward` consumes (models.py:208; at C3: 256 x 14 541 x 4 B = 14.9 MB in total).  Nothing downstream in the
+    reference reads replicated per-layer node states (models.py:157-170 uses the last hidden + query, then gathers tails,
+    :202-208), which is why the per-layer full-state gather of round 1 (953 MB per rank per layer at C3 - more bytes than
+    the layer itself moves) is no longer on the default path; `OverlappedStateGather` remains for callers that want
+    replicated states (path visualisation, base_nbfnet.py:156-172)."""
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.group = group
+
+    def local_scores(self, rel_graph, graph, h_index, r_index):
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        lo, hi = head_range(len(h_index), rank, world)
+        return self.model(rel_graph, graph, h_index[lo:hi], r_index[lo:hi])
+
+    def gather_scores(self, local, batch_size, out=None):
+        out, _ = all_gather_heads(local, batch_size, group=self.group, out=out)
+        return out
+
+    def __call__(self, rel_graph, graph, h_index, r_index):
+        """h_index, r_index: the FULL batch (B,) on every rank.  Returns the replicated (B, N) score matrix."""
+        return self.gather_scores(self.local_scores(rel_graph, graph, h_index, r_index), len(h_index))
