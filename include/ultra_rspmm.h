@@ -200,6 +200,25 @@ int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_
                             void *stream);
 
 /*
+ * Training-mode epilogue (second half).  Forward: the same tcgen05 kernel as
+ * ultra_nbfnet_update_f32 (LayerNorm always on), which additionally keeps what the backward needs:
+ *   z_out (num_rows, 64)  the Linear output W.[x;u] + bias BEFORE LayerNorm;  stats_out (num_rows, 2) = (mean, rstd) per row.
+ * Backward of  y = relu(LayerNorm(z) * gamma + beta)  in ONE pass (read out_grad and z, write z_grad):
+ *   z_grad (num_rows, 64);  partials (ultra_nbfnet_update_bwd_grid(num_rows), 3, 64): per-CTA partial sums of
+ *   [0] d gamma, [1] d beta, [2] d bias (= column sums of z_grad) - the caller sums over the first axis (fixed order:
+ *   deterministic).  The three GEMM-shaped gradients that remain - d[x;u] = z_grad . W, dW = z_grad^T . [x;u] - are plain
+ *   library GEMMs on the caller's side (ultra_b200.fused), as is the residual's pass-through of out_grad.
+ */
+int ultra_nbfnet_update_train_f32(const float *x, const float *u, const float *weight_t, const float *bias,
+                                  const float *ln_gamma, const float *ln_beta, float *out, float *z_out,
+                                  float *stats_out, int64_t num_rows, int64_t in_dim, int64_t out_dim, float ln_eps,
+                                  int relu, int shortcut, int sm_limit, void *stream);
+int ultra_nbfnet_update_bwd_grid(int64_t num_rows);
+int ultra_nbfnet_update_bwd_f32(const float *out_grad, const float *z, const float *stats, const float *ln_gamma,
+                                const float *ln_beta, float *z_grad, float *partials, int64_t num_rows, int64_t dim,
+                                int relu, void *stream);
+
+/*
  * All per-layer relation projections of the entity stack in ONE launch, fp32:
  *     out[l, m, :] = W2[l] . relu( W1[l] . x[m, :] + b1[l] ) + b2[l]          l < num_layers, m < num_rows
  * replaces the nn.Sequential(Linear(64,64), ReLU, Linear(64,64)) every entity layer applies to the SAME (B, R, 64)

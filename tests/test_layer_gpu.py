@@ -371,3 +371,70 @@ def test_inference_mode_tensors_are_accepted(cuda_device):
         ones = torch.ones(ei.shape[1], device=d)  # created inside the mode: an inference tensor
         out = generalized_rspmm(ei.to(d), et.to(d), ones, rel.to(d), x.to(d))
     assert_close_ref(out, oracle_all("add", "mul", ei, et, torch.ones(ei.shape[1]), rel, x), "inference mode")
+
+
+@pytest.mark.parametrize("relu,shortcut", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("shape", [(1, 64), (3, 50, 64), (5, 1000, 64), (2, 128 * 9 + 17, 64)])
+def test_nbfnet_update_training_forward_and_backward(cuda_device, relu, shortcut, shape):
+    """Training-mode epilogue (second half): tcgen05 forward that keeps z + LayerNorm statistics, one
+    backward kernel for ReLU + LayerNorm, library GEMMs for the rest - against PyTorch autograd in fp64."""
+    from ultra_b200.fused import nbfnet_update
+    dev = cuda_device
+    torch.manual_seed(21)
+    lin = torch.nn.Linear(128, 64).to(dev)
+    ln = torch.nn.LayerNorm(64).to(dev)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(*shape, device=dev, requires_grad=True)
+    u = (torch.randn(*shape, device=dev) * 3).requires_grad_()
+    gout = torch.randn(*shape, device=dev)
+    out = nbfnet_update(x, u, lin, ln, relu=relu, shortcut=shortcut)
+    assert out.requires_grad
+    out.backward(gout)
+    got = [x.grad, u.grad, lin.weight.grad, lin.bias.grad, ln.weight.grad, ln.bias.grad]
+    # fp64 reference through PyTorch autograd
+    xd, ud = x.detach().double().requires_grad_(), u.detach().double().requires_grad_()
+    Wd, bd = lin.weight.detach().double().requires_grad_(), lin.bias.detach().double().requires_grad_()
+    gd, btd = ln.weight.detach().double().requires_grad_(), ln.bias.detach().double().requires_grad_()
+    ref = torch.nn.functional.layer_norm(torch.nn.functional.linear(torch.cat([xd, ud], -1), Wd, bd), (64,), gd, btd, ln.eps)
+    if relu:
+        ref = torch.relu(ref)
+    if shortcut:
+        ref = ref + xd
+    ref.backward(gout.double())
+    torch.testing.assert_close(out.detach().double(), ref.detach(), rtol=1e-5, atol=2e-5)
+    for name, a, b in zip(("x", "u", "weight", "bias", "gamma", "beta"), got, (xd, ud, Wd, bd, gd, btd)):
+        scale = float(b.grad.abs().max())
+        torch.testing.assert_close(a.double(), b.grad, rtol=1e-4, atol=2e-5 * max(scale, 1.0),
+                                   msg=lambda m, name=name: "grad of %s: %s" % (name, m))
+
+
+def test_training_layer_uses_fused_epilogue_and_matches_restatement(cuda_device):
+    """One entity layer, forward + backward: fast path (head-major rspmm + training epilogue) vs the literal restatement
+    (flat rspmm + eager PyTorch epilogue), gradients of the inputs and of every parameter."""
+    from ultra_b200.layer import GeneralizedRelationalConv
+    torch.manual_seed(22)
+    dev = cuda_device
+    B, N, R, d, E = 4, 400, 11, 64, 6000
+    layer = GeneralizedRelationalConv(d, d, R, d, "distmult", "sum", layer_norm=True, project_relations=True).to(dev)
+    ei = torch.randint(0, N, (2, E), device=dev)
+    et = torch.randint(0, R, (E,), device=dev)
+    w = torch.ones(E, device=dev)
+    query = torch.randn(B, d, device=dev)
+    x0, rel0, bd = torch.randn(B, N, d, device=dev), torch.randn(B, R, d, device=dev), torch.randn(B, N, d, device=dev)
+    gout = torch.randn(B, N, d, device=dev)
+    results = []
+    try:
+        for fuse in (True, False):
+            GeneralizedRelationalConv.fuse = fuse
+            layer.zero_grad(set_to_none=True)
+            x, rel = x0.clone().requires_grad_(), rel0.clone().requires_grad_()
+            layer.relation = rel
+            out = layer(x, query, bd, ei, et, (N, N), w, shortcut=True)
+            out.backward(gout)
+            results.append([out.detach(), x.grad, rel.grad] + [p.grad.clone() for p in layer.parameters()])
+    finally:
+        GeneralizedRelationalConv.fuse = True
+    for a, b in zip(*results):
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4 * max(float(b.abs().max()), 1.0))

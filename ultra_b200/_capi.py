@@ -36,6 +36,10 @@ SYMBOLS = {
     "ultra_relation_project_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "ultra_nbfnet_update_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float, _int, _int,
                                        _int, _int, _vp]),
+    "ultra_nbfnet_update_train_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float,
+                                             _int, _int, _int, _vp]),
+    "ultra_nbfnet_update_bwd_grid": (_int, [_i64]),
+    "ultra_nbfnet_update_bwd_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "ultra_rspmm_host_staging_bytes": (_sz, [_vp, _i64, _i64, _int]),
     "ultra_rspmm_forward_host": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
 }

@@ -138,7 +138,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t 
 __global__ void __launch_bounds__(kThreads, 1)
 update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, const float *__restrict__ W,
                   const float *__restrict__ bias, const float *__restrict__ gamma, const float *__restrict__ beta,
-                  float *__restrict__ out, long long M, float eps, int layer_norm, int relu, int shortcut) {
+                  float *__restrict__ out, long long M, float eps, int layer_norm, int relu, int shortcut,
+                  float *__restrict__ z_out, float *__restrict__ stats_out) {
+    // z_out / stats_out (training forward, both or neither): the pre-LayerNorm linear output z (M, 64) and the row
+    // statistics (mean, rstd) (M, 2) that ultra_nbfnet_update_bwd_f32 consumes; nullptr for inference
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *a_st = smem;                                       // [slot][term][10 KB]
     unsigned char *w_st = smem + kSlots * kAStageBytes;               // [term][16 KB] = 192-row B operand
@@ -307,6 +310,11 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
                 v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
                 s += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
             }
+            if (z_out != nullptr && m0 + r < M) {  // training: keep z for the backward pass (64 contiguous bytes per thread)
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                    *reinterpret_cast<float4 *>(z_out + (m0 + r) * kOut + cb + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
             if (layer_norm) {  // row statistics across the 4 column groups through shared memory (fixed order)
                 red[grp * kBM + r] = s;
                 __syncthreads();
@@ -318,6 +326,8 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
                 __syncthreads();
                 const float var = (red[4 * kBM + r] + red[5 * kBM + r] + red[6 * kBM + r] + red[7 * kBM + r]) * (1.f / kOut);
                 const float rstd = 1.f / sqrtf(var + eps);
+                if (stats_out != nullptr && grp == 0 && m0 + r < M)
+                    *reinterpret_cast<float2 *>(stats_out + 2 * (m0 + r)) = make_float2(mean, rstd);
 #pragma unroll
                 for (int c = 0; c < 16; c += 4) {
                     const float4 ga = prm4[16 + ((cb + c) >> 2)], be = prm4[32 + ((cb + c) >> 2)];
@@ -352,11 +362,12 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
 
 }  // namespace ultra
 
-extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_t, const float *bias,
-                                       const float *ln_gamma, const float *ln_beta, float *out, int64_t num_rows,
-                                       int64_t in_dim, int64_t out_dim, float ln_eps, int layer_norm, int relu,
-                                       int shortcut, int sm_limit, void *stream_) {
-    using namespace ultra;
+namespace ultra {
+namespace {
+
+int launch_update(const float *x, const float *u, const float *weight_t, const float *bias, const float *ln_gamma,
+                  const float *ln_beta, float *out, float *z_out, float *stats_out, int64_t num_rows, int64_t in_dim,
+                  int64_t out_dim, float ln_eps, int layer_norm, int relu, int shortcut, int sm_limit, void *stream_) {
     using namespace ultra::tc3;
     if (in_dim != kK || out_dim != kOut) {
         set_error("nbfnet_update: only Linear(128 -> 64) (sum / mean / max aggregation, dim 64) is fused");
@@ -369,6 +380,11 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
             set_error("nbfnet_update: x, u, weight_t, out must be non-null and 16-byte aligned");
             return 1;
         }
+    if ((z_out == nullptr) != (stats_out == nullptr) || (z_out != nullptr && !layer_norm) ||
+        (reinterpret_cast<uintptr_t>(z_out) & 15) != 0 || (reinterpret_cast<uintptr_t>(stats_out) & 7) != 0) {
+        set_error("nbfnet_update (training): z_out and stats_out come together, aligned, and need layer_norm");
+        return 1;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     static thread_local int attr_dev = -1;
     int dev = 0, sms = 148;
@@ -383,8 +399,130 @@ extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const flo
     const long long tiles = (num_rows + kBM - 1) / kBM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     update_tc3_kernel<<<grid, kThreads, kSmemBytes, stream>>>(x, u, weight_t, bias, ln_gamma, ln_beta, out,
-                                                              (long long)num_rows, ln_eps, layer_norm, relu, shortcut);
+                                                              (long long)num_rows, ln_eps, layer_norm, relu, shortcut,
+                                                              z_out, stats_out);
     err = cudaGetLastError();
     if (err != cudaSuccess) { set_error(std::string("nbfnet_update launch: ") + cudaGetErrorString(err)); return 2; }
+    return 0;
+}
+
+// ---- backward of  y = relu( LayerNorm(z) * gamma + beta )  w.r.t. z, gamma, beta (and bias = sum of dz) -----------------
+// One pass: read dout and z, write dz; 16 lanes own one 64-float row (a float4 each), a warp two rows per step; the row
+// means go through 4 shuffle steps; the parameter gradients are accumulated per lane over its rows, reduced per CTA in
+// shared memory in a fixed order and written as per-CTA partials (the caller sums `grid` rows: deterministic).
+constexpr int kBwdThreads = 256;
+
+__global__ void __launch_bounds__(kBwdThreads)
+update_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ z, const float *__restrict__ stats,
+                  const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ dz,
+                  float *__restrict__ partials, long long M, int relu) {
+    __shared__ float4 red[3][kBwdThreads / 16][16];
+    const int tid = threadIdx.x, l16 = tid & 15;
+    const long long row0 = ((long long)blockIdx.x * kBwdThreads + tid) >> 4, stride = ((long long)gridDim.x * kBwdThreads) >> 4;
+    const float4 ga = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + l16) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 be = beta ? __ldg(reinterpret_cast<const float4 *>(beta) + l16) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, dbias = dg;
+    // every lane of a half-warp runs the same number of iterations (rows are per half-warp), so the shuffles are safe
+    const long long iters = (M + stride - 1) / stride;
+    for (long long it = 0; it < iters; it++) {
+        const long long row = row0 + it * stride;
+        const bool live = row < M;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), zz = g;
+        float2 st = make_float2(0.f, 1.f);
+        if (live) {
+            g = __ldcs(reinterpret_cast<const float4 *>(dout + row * 64) + l16);
+            zz = __ldcs(reinterpret_cast<const float4 *>(z + row * 64) + l16);
+            st = __ldg(reinterpret_cast<const float2 *>(stats) + row);
+        }
+        float zh[4] = {(zz.x - st.x) * st.y, (zz.y - st.x) * st.y, (zz.z - st.x) * st.y, (zz.w - st.x) * st.y};
+        const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+        float dy[4] = {g.x, g.y, g.z, g.w}, dzh[4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float y = zh[k] * gam[k] + bet[k];
+            if (relu && !(y > 0.f)) dy[k] = 0.f;  // relu'(y): 1 for y > 0 (torch convention: 0 at y == 0)
+            dzh[k] = dy[k] * gam[k];
+            s1 += dzh[k];
+            s2 += dzh[k] * zh[k];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        s1 *= (1.f / 64.f);
+        s2 *= (1.f / 64.f);
+        float o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o4[k] = st.y * (dzh[k] - s1 - zh[k] * s2);
+        if (live) {
+            __stcs(reinterpret_cast<float4 *>(dz + row * 64) + l16, make_float4(o4[0], o4[1], o4[2], o4[3]));
+            dg.x += dy[0] * zh[0]; dg.y += dy[1] * zh[1]; dg.z += dy[2] * zh[2]; dg.w += dy[3] * zh[3];
+            db.x += dy[0]; db.y += dy[1]; db.z += dy[2]; db.w += dy[3];
+            dbias.x += o4[0]; dbias.y += o4[1]; dbias.z += o4[2]; dbias.w += o4[3];
+        }
+    }
+    red[0][tid >> 4][l16] = dg;
+    red[1][tid >> 4][l16] = db;
+    red[2][tid >> 4][l16] = dbias;
+    __syncthreads();
+    if (tid < 48) {  // 3 quantities x 16 column groups: fold the 16 row-slots in order
+        const int qn = tid >> 4, cg = tid & 15;
+        float4 a = red[qn][0][cg];
+#pragma unroll
+        for (int r = 1; r < kBwdThreads / 16; r++) {
+            const float4 b = red[qn][r][cg];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        *reinterpret_cast<float4 *>(partials + ((size_t)blockIdx.x * 3 + qn) * 64 + cg * 4) = a;
+    }
+}
+
+}  // namespace
+}  // namespace ultra
+
+extern "C" int ultra_nbfnet_update_f32(const float *x, const float *u, const float *weight_t, const float *bias,
+                                       const float *ln_gamma, const float *ln_beta, float *out, int64_t num_rows,
+                                       int64_t in_dim, int64_t out_dim, float ln_eps, int layer_norm, int relu,
+                                       int shortcut, int sm_limit, void *stream_) {
+    return ultra::launch_update(x, u, weight_t, bias, ln_gamma, ln_beta, out, nullptr, nullptr, num_rows, in_dim, out_dim,
+                                ln_eps, layer_norm, relu, shortcut, sm_limit, stream_);
+}
+
+extern "C" int ultra_nbfnet_update_train_f32(const float *x, const float *u, const float *weight_t, const float *bias,
+                                             const float *ln_gamma, const float *ln_beta, float *out, float *z_out,
+                                             float *stats_out, int64_t num_rows, int64_t in_dim, int64_t out_dim,
+                                             float ln_eps, int relu, int shortcut, int sm_limit, void *stream_) {
+    if (z_out == nullptr || stats_out == nullptr) {
+        ultra::set_error("nbfnet_update_train: z_out and stats_out are required");
+        return 1;
+    }
+    return ultra::launch_update(x, u, weight_t, bias, ln_gamma, ln_beta, out, z_out, stats_out, num_rows, in_dim, out_dim,
+                                ln_eps, 1, relu, shortcut, sm_limit, stream_);
+}
+
+extern "C" int ultra_nbfnet_update_bwd_grid(int64_t num_rows) {
+    const long long want = (num_rows + 15) / 16 / (ultra::kBwdThreads / 16 * 4);  // >= 4 row-steps per thread
+    return (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+}
+
+extern "C" int ultra_nbfnet_update_bwd_f32(const float *out_grad, const float *z, const float *stats,
+                                           const float *ln_gamma, const float *ln_beta, float *z_grad, float *partials,
+                                           int64_t num_rows, int64_t dim, int relu, void *stream_) {
+    using namespace ultra;
+    if (dim != 64) { set_error("nbfnet_update_bwd: only dim == 64 is implemented"); return 1; }
+    if (num_rows < 0) { set_error("nbfnet_update_bwd: negative num_rows"); return 1; }
+    for (const void *p : {(const void *)out_grad, (const void *)z, (const void *)stats, (const void *)z_grad,
+                          (const void *)partials})
+        if (p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) != 0) {
+            set_error("nbfnet_update_bwd: pointers must be non-null and 16-byte aligned");
+            return 1;
+        }
+    const int grid = ultra_nbfnet_update_bwd_grid(num_rows);
+    update_bwd_kernel<<<grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        out_grad, z, stats, ln_gamma, ln_beta, z_grad, partials, (long long)num_rows, relu);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error(std::string("nbfnet_update_bwd launch: ") + cudaGetErrorString(err)); return 2; }
     return 0;
 }

@@ -26,8 +26,10 @@ namespace {
         }                                                                                      \
     } while (0)
 
-constexpr size_t kMetaSmem = (size_t)kCtaWarps * kMetaStageBytes;  // 32 KB of per-warp metadata staging per CTA
-constexpr size_t kSlabSmemLimit = 78 * 1024;  // tiles in smem while 2 CTAs/SM (tiles + metadata + reserve) still fit in 227 KB
+constexpr size_t kMetaSmem = (size_t)kCtaWarps * kMetaStageBytes;  // per-warp metadata staging per CTA (33 KB at 16 warps)
+// tiles in smem while kCtasPerSm CTAs (tiles + metadata + 1 KB reserved each + static smem) still fit in 227 KB: 78 KB at 512 x 2
+constexpr size_t kSlabSmemLimit = ((size_t)227 * 1024 / kCtasPerSm - kMetaSmem - 2560) / 1024 * 1024;
+static_assert(kCtasPerSm != 2 || kCtaThreads != 512 || kSlabSmemLimit == 78 * 1024, "default geometry: 78 KB of tiles");
 
 // process-wide launch tunables (ultra_rspmm_set_tunable); the SM reservation is per plan (ultra_rspmm_plan_set_sm_limit)
 std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
@@ -106,7 +108,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
 
     if (p.num_warp_items > 0) {
         const int sm_limit = plan->sm_limit;
-        const int ctas = ((sm_limit > 0 && sm_limit < plan->sm_count) ? sm_limit : plan->sm_count) * 2;
+        const int ctas = ((sm_limit > 0 && sm_limit < plan->sm_count) ? sm_limit : plan->sm_count) * kCtasPerSm;
         // items per warp per unit: 2 when that still leaves every CTA several units
         int ipw = 2;
         auto units_per_tile = [&](int k) { return (p.num_warp_items + kCtaWarps * k - 1) / (kCtaWarps * k); };
@@ -261,6 +263,45 @@ size_t scratch_bytes(const ultra_rspmm_plan *plan, int64_t dim, int dtype) {
 }  // namespace
 }  // namespace ultra
 
+// Streams / events of the host-buffer pipeline (ultra_rspmm_forward_host), owned by the plan and created lazily.
+struct ultra::HostLanes {
+    static constexpr int kMax = 4;
+    cudaStream_t in[kMax] = {}, out[kMax] = {}, k = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr, ein[2][kMax] = {}, ek[2] = {}, eout[2][kMax] = {};
+    int ready = 0;  // lanes [0, ready) exist
+    int ensure(int split) {
+        if (k == nullptr) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&k, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&ek[b], cudaEventDisableTiming));
+        }
+        for (; ready < split; ready++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&in[ready], cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&out[ready], cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                CUDA_TRY(cudaEventCreateWithFlags(&ein[b][ready], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&eout[b][ready], cudaEventDisableTiming));
+            }
+        }
+        return 0;
+    }
+    ~HostLanes() {  // pending work completes first (stream destruction is deferred by the runtime)
+        for (int i = 0; i < kMax; i++) {
+            if (in[i]) cudaStreamDestroy(in[i]);
+            if (out[i]) cudaStreamDestroy(out[i]);
+            for (int b = 0; b < 2; b++) {
+                if (ein[b][i]) cudaEventDestroy(ein[b][i]);
+                if (eout[b][i]) cudaEventDestroy(eout[b][i]);
+            }
+        }
+        if (k) cudaStreamDestroy(k);
+        if (start) cudaEventDestroy(start);
+        if (done) cudaEventDestroy(done);
+        for (int b = 0; b < 2; b++) if (ek[b]) cudaEventDestroy(ek[b]);
+    }
+};
+
 using namespace ultra;
 
 extern "C" {
@@ -313,7 +354,10 @@ int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_inde
                       workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
-void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan) { delete plan; }
+void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan) {
+    if (plan != nullptr) delete plan->host_lanes;
+    delete plan;
+}
 
 int ultra_rspmm_plan_input_sorted(const ultra_rspmm_plan *plan) { return plan ? plan->input_sorted : 0; }
 
@@ -483,39 +527,13 @@ int ultra_rspmm_forward_host(const ultra_rspmm_plan *plan, int sum_op, int mul_o
     }
     // lanes: copy-in (x split), compute, copy-out (x split); events chain them per slab and protect buffer reuse.
     // `split` > 1 issues each slab copy as `split` row blocks on separate streams so that more than one copy engine
-    // works on the strided (2 KB per row) transfers.
-    constexpr int kMax = 4;
-    struct Lanes {  // RAII: every exit path releases the streams / events (pending work completes first)
-        cudaStream_t in[kMax] = {}, out[kMax] = {}, k = nullptr;
-        cudaEvent_t start = nullptr, done = nullptr, ein[2][kMax] = {}, ek[2] = {}, eout[2][kMax] = {};
-        ~Lanes() {
-            for (int i = 0; i < kMax; i++) {
-                if (in[i]) cudaStreamDestroy(in[i]);
-                if (out[i]) cudaStreamDestroy(out[i]);
-                for (int b = 0; b < 2; b++) {
-                    if (ein[b][i]) cudaEventDestroy(ein[b][i]);
-                    if (eout[b][i]) cudaEventDestroy(eout[b][i]);
-                }
-            }
-            if (k) cudaStreamDestroy(k);
-            if (start) cudaEventDestroy(start);
-            if (done) cudaEventDestroy(done);
-            for (int b = 0; b < 2; b++) if (ek[b]) cudaEventDestroy(ek[b]);
-        }
-    } L;
-    const int split = std::max(1, std::min(g_host_copy_split.load(), kMax));
-    CUDA_TRY(cudaStreamCreateWithFlags(&L.k, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&L.start, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
-    for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&L.ek[b], cudaEventDisableTiming));
-    for (int i = 0; i < split; i++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&L.in[i], cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&L.out[i], cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            CUDA_TRY(cudaEventCreateWithFlags(&L.ein[b][i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&L.eout[b][i], cudaEventDisableTiming));
-        }
-    }
+    // works on the strided (2 KB per row) transfers.  The lanes (9 streams + 13 events at split 1) are created on the
+    // first host call of a plan and reused by every later one (round 1 created and destroyed them per call).
+    const int split = std::max(1, std::min(g_host_copy_split.load(), HostLanes::kMax));
+    ultra_rspmm_plan *mplan = const_cast<ultra_rspmm_plan *>(plan);
+    if (mplan->host_lanes == nullptr) mplan->host_lanes = new HostLanes();
+    HostLanes &L = *mplan->host_lanes;
+    if (int rc0 = L.ensure(split)) return rc0;
     CUDA_TRY(cudaEventRecord(L.start, stream));
     CUDA_TRY(cudaStreamWaitEvent(L.k, L.start, 0));
     for (int i = 0; i < split; i++) {

@@ -58,7 +58,14 @@ constexpr int kItemEdges = 64;   // max edges of a whole-segment item and chunk 
 constexpr int kMetaSubBytes = kItemEdges * 8 + ULTRA_META_PAD;
 constexpr int kMetaStageBytes = kSubPerWarp * kMetaSubBytes;
 constexpr int kMergedBit = 1 << 30;  // items[k].z flag: member of a merged group of 4 full chunks
-constexpr int kCtaThreads = 512;
+#ifndef ULTRA_CTA_THREADS
+#define ULTRA_CTA_THREADS 512  // threads per persistent CTA ...
+#endif
+#ifndef ULTRA_CTAS_PER_SM
+#define ULTRA_CTAS_PER_SM 2    // ... and resident CTAs per SM (512 x 2 and 1024 x 1 both give 32 warps/SM at 64 registers; the
+#endif                         // latter keeps ONE relation tile per SM in shared memory and so leaves L1 ~3x the capacity)
+constexpr int kCtaThreads = ULTRA_CTA_THREADS;
+constexpr int kCtasPerSm = ULTRA_CTAS_PER_SM;
 constexpr int kCtaWarps = kCtaThreads / 32;
 
 enum { FWD = 0, BWD_IN = 1, BWD_REL = 2, BWD_BOTH = 3 };
@@ -498,7 +505,7 @@ __device__ __forceinline__ void stage_rows(uint32_t smem_addr, const char *src, 
 //      for the backward passes) - small graphs such as ULTRA's relation graph (N = #relations <= ~800): every gather
 //      becomes an LDS.128 (half the L1 data-pipe cost of an LDG.128) and L2 sees only the staging traffic
 template <typename T, int MODE, int SUM, int MUL, int SM>
-__global__ void __launch_bounds__(kCtaThreads, 2) seg_reduce_kernel(const SegParams<T> p) {
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(const SegParams<T> p) {
     using N = Needs<MODE, SUM, MUL>;
     constexpr int V = VecN<T>::value;
     constexpr int TILE = kLanesPerEdge * V;

@@ -24,6 +24,8 @@ struct SegOrder {
     int num_slots = 0;
 };
 
+struct HostLanes;  // rspmm_api.cu: streams / events of the host-buffer pipeline, created on first use
+
 }  // namespace ultra
 
 struct ultra_rspmm_plan {
@@ -36,6 +38,7 @@ struct ultra_rspmm_plan {
     int input_sorted = 0;
     int device = 0;
     int sm_count = 148;
+    ultra::HostLanes *host_lanes = nullptr;  // owned; freed by ultra_rspmm_plan_destroy
     int sm_limit = 0;            // 0 = size persistent grids for every SM; >0 = leave the rest to a concurrent collective
     size_t l2_bytes = 0;
     size_t smem_optin = 0;

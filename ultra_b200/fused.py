@@ -131,17 +131,87 @@ def relation_project(rel_repr, projections):
     return out
 
 
-def nbfnet_update_ok(x, u, linear, activation):
+def nbfnet_update_ok(x, u, linear, activation, layer_norm=None):
+    """Shapes / dtypes the fused epilogue covers.  With autograd recording, the training variant (which needs LayerNorm
+    and the Linear bias) is used; otherwise the inference kernel."""
     import torch.nn.functional as F
-    return (x.is_cuda and x.dtype == torch.float32 and u.dtype == torch.float32 and x.shape == u.shape
-            and x.shape[-1] == 64 and linear.in_features == 128 and linear.out_features == 64
-            and linear.weight.dtype == torch.float32 and (activation is None or activation is F.relu)
-            and not torch.is_grad_enabled())
+    ok = (x.is_cuda and x.dtype == torch.float32 and u.dtype == torch.float32 and x.shape == u.shape
+          and x.shape[-1] == 64 and linear.in_features == 128 and linear.out_features == 64
+          and linear.weight.dtype == torch.float32 and (activation is None or activation is F.relu))
+    if ok and torch.is_grad_enabled():
+        ok = layer_norm is not None and layer_norm.elementwise_affine and linear.bias is not None
+    return ok
+
+
+class _NBFNetUpdateFunction(autograd.Function):
+    """out = (shortcut ? x : 0) + relu?( LayerNorm( [x ; u] . W^T + b ) )  with a hand-written forward AND backward
+    (layers.py:233-240 + models.py:158-160).  Forward: the tcgen05 epilogue kernel, which also stores z (the Linear
+    output) and the LayerNorm row statistics.  Backward: ONE kernel for ReLU + LayerNorm (-> dz, d gamma, d beta, d bias),
+    then the GEMM-shaped gradients as library GEMMs: d[x;u] = dz . W (two GEMMs, the residual folded into the first) and
+    dW = dz^T . [x;u] as a head-batched GEMM summed over heads."""
+
+    @staticmethod
+    def forward(ctx, x, u, weight, bias, gamma, beta, eps, relu, shortcut, sm_limit):
+        lib = _capi.lib()
+        xc, uc = x.detach().contiguous(), u.detach().contiguous()
+        out = torch.empty_like(xc)
+        z = torch.empty_like(xc)
+        rows = xc.numel() // 64
+        stats = xc.new_empty(rows, 2)
+        wt = weight.detach().t().contiguous()
+        with torch.cuda.device(x.device):
+            rc = lib.ultra_nbfnet_update_train_f32(xc.data_ptr(), uc.data_ptr(), wt.data_ptr(), bias.detach().data_ptr(),
+                                                   gamma.detach().data_ptr(), beta.detach().data_ptr(), out.data_ptr(),
+                                                   z.data_ptr(), stats.data_ptr(), rows, 128, 64, float(eps),
+                                                   1 if relu else 0, 1 if shortcut else 0, int(sm_limit),
+                                                   _stream_ptr(x.device))
+        _capi.check(rc, "ultra_nbfnet_update_train_f32")
+        ctx.save_for_backward(xc, uc, weight, gamma, beta, z, stats)
+        ctx.relu, ctx.shortcut = relu, shortcut
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        lib = _capi.lib()
+        xc, uc, weight, gamma, beta, z, stats = ctx.saved_tensors
+        og = out_grad.contiguous()
+        rows = og.numel() // 64
+        dz = torch.empty_like(og)
+        grid = lib.ultra_nbfnet_update_bwd_grid(rows)
+        partials = og.new_empty(grid, 3, 64)
+        with torch.cuda.device(og.device):
+            rc = lib.ultra_nbfnet_update_bwd_f32(og.data_ptr(), z.data_ptr(), stats.data_ptr(), gamma.detach().data_ptr(),
+                                                 beta.detach().data_ptr(), dz.data_ptr(), partials.data_ptr(), rows, 64,
+                                                 1 if ctx.relu else 0, _stream_ptr(og.device))
+        _capi.check(rc, "ultra_nbfnet_update_bwd_f32")
+        sums = partials.sum(0)  # fixed order over the CTAs: deterministic
+        dgamma, dbeta, dbias = sums[0], sums[1], sums[2]
+        dz2, og2 = dz.view(rows, 64), og.view(rows, 64)
+        w = weight.detach()
+        dx = du = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = (torch.addmm(og2, dz2, w[:, :64]) if ctx.shortcut else torch.mm(dz2, w[:, :64])).view_as(xc)
+        if ctx.needs_input_grad[1]:
+            du = torch.mm(dz2, w[:, 64:]).view_as(uc)
+        if ctx.needs_input_grad[2]:
+            # dW = dz^T . [x ; u]: reduce over rows head by head (batched GEMM over the leading dim), then over the heads
+            lead = xc.shape[0] if xc.dim() == 3 else 1
+            dz3 = dz.view(lead, -1, 64).transpose(1, 2)
+            dw = torch.cat([torch.bmm(dz3, xc.view(lead, -1, 64)).sum(0), torch.bmm(dz3, uc.view(lead, -1, 64)).sum(0)], 1)
+        return dx, du, dw, dbias, dgamma, dbeta, None, None, None, None
 
 
 def nbfnet_update(x, u, linear, layer_norm=None, relu=True, shortcut=False, sm_limit=0):
-    """One-pass layer epilogue (inference).  x, u: (..., 64) fp32 CUDA; returns a tensor of x's shape.
+    """One-pass layer epilogue.  x, u: (..., 64) fp32 CUDA; returns a tensor of x's shape.  Differentiable when autograd
+    is recording (training variant, needs layer_norm).
     sm_limit > 0 launches at most that many persistent CTAs (SMs left to a concurrent collective)."""
+    if torch.is_grad_enabled() and (x.requires_grad or u.requires_grad or linear.weight.requires_grad):
+        return _NBFNetUpdateFunction.apply(x, u, linear.weight, linear.bias, layer_norm.weight, layer_norm.bias,
+                                           layer_norm.eps, relu, shortcut, sm_limit)
+    return _nbfnet_update_inference(x, u, linear, layer_norm, relu, shortcut, sm_limit)
+
+
+def _nbfnet_update_inference(x, u, linear, layer_norm=None, relu=True, shortcut=False, sm_limit=0):
     lib = _capi.lib()
     xc, uc = x.contiguous(), u.contiguous()
     out = torch.empty_like(xc)

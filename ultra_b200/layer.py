@@ -67,7 +67,7 @@ class GeneralizedRelationalConv(nn.Module):
         if fast:
             update = self.message_and_aggregate_heads(edge_index, input, relation, boundary, edge_type, edge_weight,
                                                       size[0])
-            if fused.nbfnet_update_ok(input, update, self.linear, self.activation):
+            if fused.nbfnet_update_ok(input, update, self.linear, self.activation, self.layer_norm):
                 from .plan import plan_cache
                 plan = plan_cache.get(edge_index, edge_type, input.shape[1], relation.shape[1])  # cache hit
                 return fused.nbfnet_update(input, update, self.linear, self.layer_norm,
