@@ -114,3 +114,34 @@ def test_ultra_nbfnet_runner_matches_fixture(fx, monkeypatch):
         all_scores = model(rel_graph, graph, t("h_index"), t("r_index"))  # every entity as the tail
         assert all_scores.shape == (4, int(fx["num_node"]))
         close(all_scores.gather(1, t("t_index")), fx["score"], "score_all at the fixture's tails", tol=5e-5)
+
+
+def test_merge_parallel_edges_preserves_the_sum_aggregate():
+    """merge_parallel_edges: (sum_t rel[t]) * x[j] over merged edges == sum over the original parallel edges (oracle on
+    both graphs), for a random multigraph where node pairs carry arbitrary subsets of the 4 types; a graph with a
+    duplicated (pair, type) edge is refused (every copy counts in the reference)."""
+    from ultra_b200.nbfnet import merge_parallel_edges
+    g = torch.Generator().manual_seed(9)
+    n, R, d = 30, 4, 16
+    pairs = torch.randint(0, n, (2, 300), generator=g)
+    pairs = torch.unique(pairs[0] * n + pairs[1])
+    rows, cols, types = [], [], []
+    for key in pairs.tolist():
+        subset = torch.nonzero(torch.rand(R, generator=g) < 0.5).flatten().tolist() or [int(torch.randint(0, R, (1,), generator=g))]
+        for t in subset:
+            rows.append(key // n); cols.append(key % n); types.append(t)
+    ei, et = torch.tensor([rows, cols]), torch.tensor(types)
+    perm = torch.randperm(ei.shape[1], generator=g)
+    ei, et = ei[:, perm], et[perm]
+    mei, met, combos = merge_parallel_edges(ei, et, R)
+    assert mei.shape[1] == pairs.numel() and combos.shape[1] == R and int(met.max()) + 1 == combos.shape[0]
+    rel, x = torch.randn(R, d, generator=g), torch.randn(n, d, generator=g)
+
+    def run(e_i, e_t, relation):
+        w = torch.ones(e_i.shape[1])
+        sei, stt, sw, _ = oracle.sort_edges(e_i.numpy(), e_t.numpy(), w.numpy())
+        return torch.from_numpy(oracle.c_forward("add", "mul", sei, stt, sw, relation.numpy(), x.numpy()))
+    exp, got = run(ei, et, rel), run(mei, met, combos @ rel)
+    torch.testing.assert_close(got, exp, rtol=1e-5, atol=1e-5 * float(exp.abs().max()))
+    dup_ei, dup_et = torch.cat([ei, ei[:, :1]], 1), torch.cat([et, et[:1]])
+    assert merge_parallel_edges(dup_ei, dup_et, R) is None

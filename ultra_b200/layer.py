@@ -51,7 +51,7 @@ class GeneralizedRelationalConv(nn.Module):
         batch_size = len(query)
         shared = False  # relation is ONE (R, d) block for every head (embedding mode, layers.py:76)
         if relation is not None:
-            pass
+            shared = relation.dim() == 2  # one (R', d) block for every head (e.g. the merged relation-graph table)
         elif self.dependent:
             relation = self.relation_linear(query).view(batch_size, self.num_relation, self.input_dim)
         elif not self.project_relations:
