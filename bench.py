@@ -444,7 +444,7 @@ def main():
     strong = None
     if not args.no_strong:
         strong = []
-        for cfg in ("C3", "C4"):
+        for cfg in ("C3", "C3-b16", "C4"):
             try:
                 strong.append(bench_strong(cfg, device, world, rank, dist, timeit))
             except Exception as exc:  # noqa: BLE001 - extras only (every rank takes the same path: shapes are static)
@@ -570,6 +570,9 @@ STRONG = {
     # BASELINE configs[2]: FB15k-237 inductive-scale KG, full relation-graph + entity-graph stack, batch 256
     "C3": dict(scale="fb15k237", batch=256, seed=1234 + 3,
                what="BASELINE configs[2]: FB15k-237-scale KG + its relation graph, full Ultra forward, batch 256"),
+    # the launch-bound end of the same configuration: 16 queries in total
+    "C3-b16": dict(scale="fb15k237", batch=16, seed=1234 + 3,
+                   what="BASELINE configs[2] at batch 16: FB15k-237-scale KG + its relation graph, full Ultra forward"),
     # BASELINE configs[3]: CoDEx-L scale (77,951 nodes, 1.1 M edges), 6 layers, batch 64 (8 per GPU at 8 GPUs)
     "C4": dict(scale="codex_l", batch=64, seed=1234 + 4,
                what="BASELINE configs[3]: CoDEx-L-scale KG + its relation graph, full Ultra forward, batch 64"),
