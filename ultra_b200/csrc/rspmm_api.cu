@@ -97,7 +97,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     }
 
     SegParams<T> p;
-    p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.nonempty = so.nonempty; p.items = so.items;
+    p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.sched = plan->sched + 2 * ORD; p.nonempty = so.nonempty; p.items = so.items;
     p.num_warp_items = so.num_items / kSubPerWarp;
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
     p.dst = dst; p.rgrad = rgrad; p.partial = scratch; p.boundary = boundary; p.lay = lay;

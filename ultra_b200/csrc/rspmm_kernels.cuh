@@ -170,6 +170,7 @@ template <typename T> struct SegParams {
     const int2 *meta;
     const T *w;  // per-edge weight in this order, or nullptr = all ones
     const int *w_nonunit;  // device flag written by set_edge_weight: 0 -> every weight == 1 (skip the loads)
+    int *sched;            // {next block ticket, CTAs finished}: dynamic tile-major work queue, reset by the last CTA
     const int *nonempty;
     const int4 *items;
     int num_warp_items;
@@ -528,7 +529,17 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
     const bool use_w = p.w != nullptr && __ldg(p.w_nonunit) != 0;  // uniform over the grid
     int cur_tile = -1;
 
-    for (long long blk = blockIdx.x; blk * p.run < p.total_units; blk += gridDim.x) {
+    // Work queue: blocks of `run` consecutive units are handed out in tile-major order by a global ticket counter, so a
+    // CTA that drew short items simply takes the next block (static round-robin left a ~1/waves tail: 15 % at 32 heads
+    // per GPU, where a CTA only sees ~5 blocks).  The order in which tiles are visited - what keeps the gathered tiles
+    // L2-resident - is unchanged.  Results do not depend on which CTA computes a unit.
+    __shared__ int s_ticket;
+    for (;;) {
+        __syncthreads();  // everyone has read the previous ticket
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
+        __syncthreads();
+        const long long blk = s_ticket;
+        if (blk * p.run >= p.total_units) break;
         for (int uu = 0; uu < p.run; uu++) {
             const long long unit = blk * p.run + uu;
             if (unit >= p.total_units) break;
@@ -568,6 +579,14 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
                 const int wi = (chunk * p.items_per_warp + k) * kCtaWarps + warp;
                 if (wi < p.num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, meta_s_addr, use_w);
             }
+        }
+    }
+    // the last CTA to leave resets the queue for the next launch on this plan (launches of one plan are stream-ordered)
+    if (threadIdx.x == 0) {
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
         }
     }
 }

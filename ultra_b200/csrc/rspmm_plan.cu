@@ -57,7 +57,7 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R, int item_edges) {
     L.keysB = take((size_t)E * 8);
     L.valsA = take((size_t)E * 4);
     L.valsB = take((size_t)E * 4);
-    L.flags = take(16);
+    L.flags = take(64);  // [0] range error, [1] unsorted, [2] w_nonunit, [4..9] work-queue tickets of the three orders
     L.cub_temp_bytes = (size_t)(1 << 20) + (size_t)E;
     L.cub_temp = take(L.cub_temp_bytes);
     L.total = off;
@@ -261,11 +261,12 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
     auto *valsB = reinterpret_cast<int *>(ws + L.valsB);
     int *flags = reinterpret_cast<int *>(ws + L.flags);
     plan->w_nonunit = flags + 2;
+    plan->sched = flags + 4;
 
     const int threads = 256;
     const int blocks = (int)((E + threads - 1) / threads);
     int h_flags[4] = {0, 0, 0, 0};
-    CUDA_TRY(cudaMemsetAsync(flags, 0, 16, stream));
+    CUDA_TRY(cudaMemsetAsync(flags, 0, 64, stream));
     if (E > 0) {
         validate_kernel<<<blocks, threads, 0, stream>>>(edge_index, edge_type, N, E, R, flags);
         CUDA_TRY(cudaGetLastError());

@@ -33,6 +33,7 @@ struct ultra_rspmm_plan {
     ultra::SegOrder ord[3];  // FWD (by row), BWD_IN (by col), BWD_REL (by relation)
     int *row_of_edge = nullptr;  // (E) row of each edge in FWD order (weight_grad kernel)
     int *w_nonunit = nullptr;    // device flag: some bound weight != 1
+    int *sched = nullptr;        // (3 orders x 2) device work-queue tickets {next block, CTAs done}; self-resetting
     bool unit_weight = true;
     int w_dtype = -1;
     int input_sorted = 0;
