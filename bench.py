@@ -74,6 +74,17 @@ def load_counters():
     return {}
 
 
+L2_GATHER_PEAK_GBS = 7164.5  # best LDG.128 row-gather rate of tools/gather_microbench.cu (profiles/r01_gather_microbench.jsonl)
+
+
+def l2_gather(counters, ms):
+    if not counters or not counters.get("l2_to_l1_bytes"):
+        return None
+    achieved = counters["l2_to_l1_bytes"] / (ms * 1e-3) / 1e9
+    return {"achieved": achieved, "peak": L2_GATHER_PEAK_GBS, "unit": "GB/s", "frac": achieved / L2_GATHER_PEAK_GBS,
+            "bytes_per_launch": counters["l2_to_l1_bytes"], "l1_hit_rate": counters.get("l1_hit_rate")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -424,7 +435,20 @@ def main():
         # edge-gather model of the backward: per edge one output_grad row slice for input_grad and (two-pass default) one
         # output_grad + one input row slice for relation_grad; input_grad and relation_grad written once; relation read once
         bwd_bytes = 4 * D * (3 * E + N + 2 * R) + 2 * 12 * E + 4 * (N + R + 2)
+        _capi.set_tunable("bwd_fused_relgrad", 1)
+        try:
+            fused_ms = timeit(bwd, reps=5, warm=2, collective=False)
+        finally:
+            _capi.set_tunable("bwd_fused_relgrad", 0)
+        cb = counters.get("backward_in"), counters.get("backward_rel")
+        l2b = None
+        if cb[0] and cb[1]:
+            l2b = l2_gather({"l2_to_l1_bytes": cb[0]["l2_to_l1_bytes"] + cb[1]["l2_to_l1_bytes"]}, bwd_ms)
         backward_info = {"ms_per_call": bwd_ms, "calls": 5, "ratio_to_forward": bwd_ms / (sum(per_step) / len(per_step)),
+                         "fused_relgrad_ms_per_call": fused_ms, "l2_gather": l2b,
+                         "fused_note": "opt-in one-pass backward (tunable bwd_fused_relgrad): relation_grad by vector "
+                                       "reductions at L2, order-dependent in its last bits like the reference's atomicAdd "
+                                       "backward; wins on uniform relation frequencies, loses on Zipf",
                          "what": "ultra_rspmm_backward add-mul, same workload: input_grad + relation_grad, no atomics",
                          "roofline": {"bound": "hbm", "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "peak": peak,
                                       "unit": "GB/s", "frac": bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak,
@@ -473,6 +497,10 @@ def main():
                          # peak; pipe utilisations as captured (percent of peak sustained, same kernel build)
                          "dram_frac": (dram / (kernel_ms * 1e-3) / 1e9 / peak) if dram else None,
                          "l1tex_lsu_frac": fwd_c.get("l1tex_lsu_frac"), "l2_frac": fwd_c.get("l2_frac"),
+                         # what actually bounds the kernel: bytes L1 pulls from L2 (ncu lts__t_sectors_srcunit_tex_op_read of
+                         # the capture) over THIS run's duration, against the measured ceiling for random 128-byte row
+                         # gathers out of an L2-resident tile (tools/gather_microbench.cu, profiles/r01_gather_microbench.jsonl)
+                         "l2_gather": l2_gather(fwd_c, kernel_ms),
                          "counters_source": fwd_c.get("source")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * D * (N + R),
                     "d2h_bytes_per_step": 4 * D * N, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,

@@ -14,7 +14,8 @@
  *   - the library owns NO device memory: the caller allocates every device buffer (workspace, scratch,
  *     outputs).  Plans are small host objects holding pointers into the caller's workspace.
  *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*); forward/backward
- *     never synchronise the host and are CUDA-graph capturable.  plan_build synchronises `stream` once.
+ *     never synchronise the host and are CUDA-graph capturable.  plan_build synchronises `stream` exactly once, at its
+ *     end (sorts, CSR construction and the work-item cutter all run on the device).
  *   - dtype: ULTRA_RSPMM_F32 or ULTRA_RSPMM_F64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES,
  *     rspmm.cu:251,313,332).  Indices are int64 at the boundary (reference convention, rspmm.cpp:22),
  *     int32 inside the plan.
@@ -45,9 +46,6 @@ const char *ultra_rspmm_version(void);
  * Process-wide launch tunables (experiment knobs; nothing on the data path depends on them being set).
  * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
  * "host_copy_split": row blocks per slab copy in forward_host.
- * "item_edges": edges per work item of the plans built (and workspaces sized) afterwards: 64 (the kernels' staging
- * capacity), 32 or 16 - finer items for calls so small that 64-edge items leave a nearly empty second wave of warps;
- * 0 (default) = chosen per plan from the edge count.
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a
  * 16-byte vector reduction at L2 (red.global.add.v4.f32), like the reference's atomicAdd backward (rspmm.cu:198-209):
@@ -58,7 +56,7 @@ const char *ultra_rspmm_version(void);
 int ultra_rspmm_set_tunable(const char *name, int value);
 
 /*
- * Host-only (no GPU needed): run the plan's work-item cutter on a CSR segment pointer (num_seg + 1 ints) and return
+ * Host-only (no GPU needed): run the HOST MIRROR of the plan's device-side work-item cutter on a CSR segment pointer (num_seg + 1 ints) and return
  * items (int4 {e_begin, e_end, j0 | merged_bit(1<<30), slot}), the fix list (int4 {segment, slot_begin, slot_count, 0};
  * the first num_fix_long entries are long segments, the rest empty ones) and the non-empty segment ids.  Exists so
  * that the CPU test-suite can check the partition invariants; not used by the product path.
@@ -66,6 +64,14 @@ int ultra_rspmm_set_tunable(const char *name, int value);
 int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items,
                                 int *fix_out, int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots,
                                 int *nonempty_out, int64_t nonempty_cap, int *num_nonempty);
+
+/*
+ * Test hook: copy one array of a built plan to the host (synchronous).  order: 0 by row, 1 by col, 2 by relation;
+ * what: 0 items (int4 x plan_info items), 1 fix list (int4), 2 non-empty segment ids (num_seg + 1 ints, entries past
+ * the count are unspecified), 3 segment pointer (num_seg + 1 ints).  The GPU test-suite compares these with the host
+ * mirror (ultra_rspmm_debug_cut_items); not used by the product path.
+ */
+int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int what, void *host_out, int64_t cap_bytes);
 
 /* Message of the last failing call on this thread ("" if none). */
 const char *ultra_rspmm_last_error(void);
@@ -101,7 +107,9 @@ int ultra_rspmm_plan_set_sm_limit(ultra_rspmm_plan *plan, int sm_limit);
 int ultra_rspmm_plan_input_sorted(const ultra_rspmm_plan *plan);
 
 /* Plan facts: what=0 num_node, 1 num_edge, 2 num_relation, 3 fwd work items, 4 fwd partial slots,
- * 5 input_grad partial slots, 6 relation_grad partial slots, 7 SM count used for grid sizing. */
+ * 5 input_grad partial slots, 6 relation_grad partial slots, 7 SM count used for grid sizing,
+ * 8 / 9 input_grad / relation_grad work items, 10 + 3 * order + {0, 1, 2}: fix entries, long-segment fix entries, segments
+ * of that order. */
 int64_t ultra_rspmm_plan_info(const ultra_rspmm_plan *plan, int what);
 
 /* Bytes of device scratch (split-row partials) forward/backward need for feature width `dim`. */

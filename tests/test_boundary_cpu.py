@@ -108,22 +108,15 @@ def test_product_never_imports_oracle():
 def test_tunables_are_host_only_and_validated(capi):
     """ultra_rspmm_set_tunable needs no GPU; unknown names / values are rejected with a message (include/ultra_rspmm.h)."""
     from ultra_b200 import _capi
-    for name, value in (("l2_percent", 25), ("host_copy_split", 1), ("bwd_fused_relgrad", 1), ("bwd_fused_relgrad", 0),
-                        ("item_edges", 16), ("item_edges", 64)):
+    for name, value in (("l2_percent", 25), ("host_copy_split", 1), ("bwd_fused_relgrad", 1), ("bwd_fused_relgrad", 0)):
         _capi.set_tunable(name, value)
     with pytest.raises(RuntimeError, match="unknown tunable"):
         _capi.set_tunable("no_such_knob", 1)
     with pytest.raises(RuntimeError, match="unknown tunable"):  # round 1's process-global SM reservation is gone:
         _capi.set_tunable("sm_limit", 140)                      # it is a per-plan field now (plan_set_sm_limit)
     assert _capi.lib().ultra_rspmm_plan_set_sm_limit(None, 140) != 0  # null plan -> error code, no crash
-    with pytest.raises(RuntimeError, match="item_edges must be"):
-        _capi.set_tunable("item_edges", 48)
-    # finer items need a larger item array: the workspace size follows the tunable
-    base = _capi.lib().ultra_rspmm_plan_workspace_bytes(14541, 544230, 474)
-    _capi.set_tunable("item_edges", 16)
-    assert _capi.lib().ultra_rspmm_plan_workspace_bytes(14541, 544230, 474) > base
-    _capi.set_tunable("item_edges", 64)
-    assert _capi.lib().ultra_rspmm_plan_workspace_bytes(14541, 544230, 474) == base
+    with pytest.raises(RuntimeError, match="unknown tunable"):  # measured in round 2 (no gain at any size) and removed
+        _capi.set_tunable("item_edges", 16)
 
 
 def test_plain_c_consumer(capi, tmp_path):

@@ -97,24 +97,6 @@ def test_cuda_matches_oracle(cuda_device, shape, sum, mul):
     check_against(sum, mul, ours, expected)
 
 
-@pytest.mark.parametrize("item_edges", [32, 16])
-@pytest.mark.parametrize("shape", SHAPES[:3] + SHAPES[4:6] + SHAPES[8:], ids=lambda s: "N%d_E%d_D%d" % (s[1], s[2], s[4]))
-@pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "add"), ("min", "mul")])
-def test_cuda_matches_oracle_with_finer_items(cuda_device, shape, sum, mul, item_edges):
-    from ultra_b200 import _capi
-    from ultra_b200.plan import plan_cache
-    seed, N, E, R, D, dtype, hub, unit = shape
-    ei, et, w, rel, x, og = random_case(seed, N, E, R, D, dtype=dtype, hub=hub, unit_weight=unit)
-    plan_cache.clear()  # plans are cut at build time
-    _capi.set_tunable("item_edges", item_edges)
-    try:
-        ours = run_ours(sum, mul, ei, et, w, rel, x, og)
-    finally:
-        _capi.set_tunable("item_edges", 64)
-        plan_cache.clear()
-    check_against(sum, mul, ours, oracle_all(sum, mul, ei, et, w, rel, x, og))
-
-
 @pytest.mark.parametrize("sum,mul", OPS)
 def test_function_apply_presorted_and_assert(cuda_device, sum, mul):
     """RSPMM*Function.apply is the reference's inner surface: pre-sorted edges, AssertionError otherwise."""

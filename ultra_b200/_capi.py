@@ -20,6 +20,7 @@ SYMBOLS = {
     "ultra_rspmm_set_tunable": (_int, [ctypes.c_char_p, _int]),
     "ultra_rspmm_plan_set_sm_limit": (_int, [_vp, _int]),
     "ultra_rspmm_debug_cut_items": (_int, [_vp, _int, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "ultra_rspmm_plan_debug_read": (_int, [_vp, _int, _int, _vp, _i64]),
     "ultra_rspmm_plan_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ultra_rspmm_plan_build": (_int, [ctypes.POINTER(_vp), _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_plan_destroy": (None, [_vp]),

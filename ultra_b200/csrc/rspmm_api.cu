@@ -314,11 +314,7 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    if (n == "item_edges") {
-        if (set_item_edges(value)) { set_error("set_tunable: item_edges must be 64 (default), 32 or 16"); return 1; }
-        return 0;
-    }
-    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, item_edges)");
+    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad)");
     return 1;
 }
 
@@ -337,6 +333,23 @@ int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out,
     }
     return cut_items_host(seg_ptr, num_seg, items_out, items_cap, num_items, fix_out, fix_cap, num_fix, num_fix_long,
                           num_slots, nonempty_out, nonempty_cap, num_nonempty);
+}
+
+int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int what, void *host_out, int64_t cap_bytes) {
+    if (plan == nullptr || order < 0 || order > 2 || host_out == nullptr) { set_error("plan_debug_read: bad arguments"); return 1; }
+    const SegOrder &so = plan->ord[order];
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case 0: src = so.items; bytes = (size_t)so.num_items * 16; break;
+        case 1: src = so.fix; bytes = (size_t)so.num_fix * 16; break;
+        case 2: src = so.nonempty; bytes = (size_t)(so.num_seg + 1) * 4; break;
+        case 3: src = so.seg_ptr; bytes = (size_t)(so.num_seg + 1) * 4; break;
+        default: set_error("plan_debug_read: what must be 0 (items), 1 (fix), 2 (nonempty), 3 (seg_ptr)"); return 1;
+    }
+    if ((int64_t)bytes > cap_bytes) { set_error("plan_debug_read: host buffer too small"); return 1; }
+    if (bytes > 0) CUDA_TRY(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 const char *ultra_rspmm_last_error(void) { return g_last_error.c_str(); }
@@ -372,6 +385,13 @@ int64_t ultra_rspmm_plan_info(const ultra_rspmm_plan *plan, int what) {
         case 5: return plan->ord[1].num_slots;
         case 6: return plan->ord[2].num_slots;
         case 7: return plan->sm_count;
+        case 8: return plan->ord[1].num_items;
+        case 9: return plan->ord[2].num_items;
+    }
+    if (what >= 10 && what < 19) {
+        const SegOrder &so = plan->ord[(what - 10) / 3];
+        const int k = (what - 10) % 3;
+        return k == 0 ? so.num_fix : (k == 1 ? so.num_fix_long : so.num_seg);
     }
     return -1;
 }

@@ -5,10 +5,11 @@
 // Three stable radix sorts (CUB, device) give the by-row / by-col / by-relation edge orders as int32 CSR;
 // the edge-balanced work-item lists are cut on the host from the three segment-pointer arrays.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
-#include <atomic>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "rspmm_kernels.cuh"
@@ -19,26 +20,27 @@ namespace ultra {
 namespace {
 
 constexpr size_t kAlign = 256;
+constexpr int kCutBlock = 64;    // segments per cutter thread (see cut_walk_block)
+constexpr int kPlanCounts = 8;   // ints per order in the device-side result block (cut_finalize_kernel)
+struct CutCounts { int whole, groups, chunks, slots, nlong, nempty, nonempty; };  // per cutter block / running totals
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 inline int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     int b = 1;
     while ((int64_t(1) << b) < n) b++;
     return b;
 }
-// Edges per work item (tunable "item_edges": 64 = kItemEdges, the kernels' staging capacity and the default; 32 / 16
-// cut finer items for calls so small that 64-edge items leave a second, nearly empty wave of warps - WN18RR x 4 heads
-// is 344 work units on 296 CTAs).  Read when the workspace is sized AND when the plan is built; a plan built with a
-// workspace sized for a coarser setting fails the size check instead of overflowing.
-std::atomic<int> g_item_edges{kItemEdges};
-// whole items <= 2E/L+1; chunks <= E/L + #long with #long <= E/L
-inline int64_t max_items(int64_t E, int L) { return 4 * ((E + L - 1) / L) + 8; }
+// item capacity: whole items <= 2E/64 + 1 (two consecutive overflow-closed items hold > 64 edges) + one forced close per
+// cutter block and per long segment; chunk items <= E/64 + #long; group items <= E/64; #long <= E/65
+inline int64_t max_items(int64_t E, int64_t S) { return 5 * ((E + kItemEdges - 1) / kItemEdges) + S / kCutBlock + 16; }
 
 struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
+    size_t cut_cnt, cut_incl, rkeys[2], ritems[2], counts;  // device cutter temporaries + per-order result counts
+    int64_t max_blocks, rest_cap;
 };
 
-WsLayout make_layout(int64_t N, int64_t E, int64_t R, int item_edges) {
+WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
     WsLayout L;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(std::max<size_t>(bytes, 16)); return o; };
@@ -48,7 +50,7 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R, int item_edges) {
         L.eid[o] = take((size_t)E * 4);
         L.seg_ptr[o] = take((size_t)(S[o] + 1) * 4);
         L.nonempty[o] = take((size_t)(S[o] + 1) * 4);
-        L.items[o] = take((size_t)max_items(E, item_edges) * 16);
+        L.items[o] = take((size_t)max_items(E, S[o]) * 16);
         L.fix[o] = take((size_t)std::max<int64_t>(S[o], 1) * 16);
         L.w[o] = take((size_t)E * 8);
     }
@@ -60,6 +62,16 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R, int item_edges) {
     L.flags = take(64);  // [0] range error, [1] unsorted, [2] w_nonunit, [4..9] work-queue tickets of the three orders
     L.cub_temp_bytes = (size_t)(1 << 20) + (size_t)E;
     L.cub_temp = take(L.cub_temp_bytes);
+    const int64_t Smax = std::max(N, R);
+    L.max_blocks = (Smax + kCutBlock - 1) / kCutBlock + 1;
+    L.rest_cap = max_items(E, Smax);
+    L.cut_cnt = take((size_t)L.max_blocks * sizeof(CutCounts));
+    L.cut_incl = take((size_t)L.max_blocks * sizeof(CutCounts));
+    for (int k = 0; k < 2; k++) {
+        L.rkeys[k] = take((size_t)L.rest_cap * 8);
+        L.ritems[k] = take((size_t)L.rest_cap * 16);
+    }
+    L.counts = take(3 * kPlanCounts * sizeof(int));
     L.total = off;
     return L;
 }
@@ -81,14 +93,17 @@ __global__ void validate_kernel(const int64_t *__restrict__ ei, const int64_t *_
 // all warps sweep the gathered matrix from low to high rows roughly in step, which is what gives the gathers their
 // L1/L2 temporal locality (measured: grouping by relation type instead costs +40% forward time on a uniform graph).
 __global__ void make_keys_kernel(int order, const int64_t *__restrict__ ei, const int64_t *__restrict__ et,
-                                 int64_t E, int sec_bits, unsigned long long *keys, int *vals) {
+                                 int64_t E, int64_t N, int64_t R, int sec_bits, unsigned long long *keys, int *vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const unsigned long long row = (unsigned long long)ei[e], col = (unsigned long long)ei[E + e];
+    // out-of-range values (flagged by validate_kernel; the plan is rejected at the end of the build) are clamped here so
+    // that the kernels enqueued behind this one stay inside their buffers without an early host synchronisation
+    auto clampi = [](int64_t v, int64_t hi) { return (unsigned long long)(v < 0 ? 0 : (v >= hi ? hi - 1 : v)); };
+    const unsigned long long row = clampi(ei[e], N), col = clampi(ei[E + e], N);
     unsigned long long pri, sec;
     if (order == 0) { pri = row; sec = col; }
     else if (order == 1) { pri = col; sec = row; }
-    else { pri = (unsigned long long)et[e]; sec = row; }
+    else { pri = clampi(et[e], R); sec = row; }
     keys[e] = (pri << sec_bits) | sec;
     vals[e] = (int)e;
 }
@@ -126,88 +141,223 @@ __global__ void build_meta_kernel(int order, const unsigned long long *__restric
         }                                                                                      \
     } while (0)
 
-// Cut one segment-pointer array into work items (host).
-//   * whole segments are packed greedily up to kItemEdges edges per item              {e0, e1, j0,  -1}
-//   * a segment longer than kItemEdges is cut into 64-edge chunks.  Every run of 4 FULL chunks becomes a merged
-//     group walked by one warp and combined with shuffles: leader {e0, e1, j|kMergedBit, slot}, followers {.., .., j|kMergedBit, -2};
-//     the remaining (<= 3 full + 1 partial) chunks are single chunk items            {e0, e1, j,  slot}
-//   Partial slots of one segment are consecutive and in edge order (groups, then single chunks).
+// ---------------------------------------------------------------------------------------------------------------------
+// Work-item cutter.  One rule, two executors: the device kernels below (the product path: plan_build never cuts on the
+// host any more) and a host mirror of the same functions (ultra_rspmm_debug_cut_items, CPU test-suite).
+//   * the segment array is processed in blocks of kCutBlock (64) segments, one thread each; a block's whole-segment
+//     items never reach into the next block (costs < 1 extra item per 64 segments and makes the greedy packing parallel)
+//   * whole segments are packed greedily up to kItemEdges edges per item                       {e0, e1, j0,  -1}
+//   * a segment longer than kItemEdges is cut into 64-edge chunks.  Every run of 4 FULL chunks becomes a merged group
+//     walked by one warp and combined with shuffles: leader {e0, e1, j|kMergedBit, slot}, followers {.., .., j|kMergedBit, -2};
+//     the remaining (<= 3 full + 1 partial) chunks are single chunk items                     {e0, e1, j,  slot}
+//     Partial slots of one segment are consecutive and in edge order (groups, then single chunks).
 // Item order: merged groups first (a multiple of 4, so a warp never mixes a group with other items), then all other
-// items longest first, so the 4 items a warp walks in lock-step have (nearly) equal lengths.
-// fix list: long segments first, then empty segments.
-void cut_items(const std::vector<int> &ptr, std::vector<int4> &items, std::vector<int> &nonempty,
-               std::vector<int4> &fix, int &num_slots, int &num_fix_long, const int kItemEdges) {  // shadows the constant
-    const int S = (int)ptr.size() - 1;
-    const int kGroupEdges = kItemEdges * kSubPerWarp;
-    std::vector<int4> groups, rest, fix_empty;
-    items.clear(); nonempty.clear(); fix.clear();
-    num_slots = 0;
-    int cur_begin = -1, cur_end = -1, cur_j0 = 0;
-    auto close = [&]() {
-        if (cur_begin >= 0) rest.push_back(make_int4(cur_begin, cur_end, cur_j0, -1));
-        cur_begin = -1;
-    };
-    for (int s = 0; s < S; s++) {
+// items by (length descending, first edge ascending), so the 4 items a warp walks in lock-step have (nearly) equal
+// lengths; padded with empty items to a multiple of 4.  fix list: long segments (in order), then empty segments.
+template <typename V>
+__host__ __device__ inline void cut_walk_block(const int *ptr, int s0, int s1, V &v) {
+    int cur_begin = -1, cur_end = -1, cur_j = 0, nj = 0;  // nj: non-empty segments of this block seen so far
+    for (int s = s0; s < s1; s++) {
         const int b = ptr[s], e = ptr[s + 1], deg = e - b;
-        if (deg == 0) { fix_empty.push_back(make_int4(s, 0, 0, 0)); continue; }
-        const int j = (int)nonempty.size();
-        nonempty.push_back(s);
+        if (deg == 0) { v.empty(s); continue; }
+        const int j = nj++;
+        v.nonempty(s);
         if (deg > kItemEdges) {
-            close();
-            const int slot0 = num_slots;
-            int c = b;
-            for (; c + kGroupEdges <= e; c += kGroupEdges) {
-                for (int k = 0; k < kSubPerWarp; k++)
-                    groups.push_back(make_int4(c + k * kItemEdges, c + (k + 1) * kItemEdges, j | kMergedBit, k ? -2 : num_slots));
-                num_slots++;
-            }
-            for (; c < e; c += kItemEdges) rest.push_back(make_int4(c, std::min(c + kItemEdges, e), j, num_slots++));
-            fix.push_back(make_int4(s, slot0, num_slots - slot0, 0));
+            if (cur_begin >= 0) { v.whole(cur_begin, cur_end, cur_j); cur_begin = -1; }
+            v.long_seg(s, b, e, j);
         } else {
-            if (cur_begin >= 0 && (e - cur_begin) > kItemEdges) close();
-            if (cur_begin < 0) { cur_begin = b; cur_j0 = j; }
+            if (cur_begin >= 0 && e - cur_begin > kItemEdges) { v.whole(cur_begin, cur_end, cur_j); cur_begin = -1; }
+            if (cur_begin < 0) { cur_begin = b; cur_j = j; }
             cur_end = e;
         }
     }
-    close();
-    std::stable_sort(rest.begin(), rest.end(),
-                     [](const int4 &a, const int4 &b) { return (a.y - a.x) > (b.y - b.x); });
-    items = groups;
-    items.insert(items.end(), rest.begin(), rest.end());
-    while (items.size() % kSubPerWarp) items.push_back(make_int4(0, 0, 0, -1));
-    num_fix_long = (int)fix.size();
-    fix.insert(fix.end(), fix_empty.begin(), fix_empty.end());
-    nonempty.push_back(0);  // pad: the walker prefetches nonempty[j+1]
+    if (cur_begin >= 0) v.whole(cur_begin, cur_end, cur_j);
+}
+
+__host__ __device__ inline CutCounts cut_add(const CutCounts &a, const CutCounts &b) {
+    CutCounts r;
+    r.whole = a.whole + b.whole; r.groups = a.groups + b.groups; r.chunks = a.chunks + b.chunks;
+    r.slots = a.slots + b.slots; r.nlong = a.nlong + b.nlong; r.nempty = a.nempty + b.nempty;
+    r.nonempty = a.nonempty + b.nonempty;
+    return r;
+}
+struct CutSum {
+    __host__ __device__ CutCounts operator()(const CutCounts &a, const CutCounts &b) const { return cut_add(a, b); }
+};
+
+struct CountVisitor {
+    CutCounts c{0, 0, 0, 0, 0, 0, 0};
+    __host__ __device__ void empty(int) { c.nempty++; }
+    __host__ __device__ void nonempty(int) { c.nonempty++; }
+    __host__ __device__ void whole(int, int, int) { c.whole++; }
+    __host__ __device__ void long_seg(int, int b, int e, int) {
+        const int deg = e - b, groups = deg / (kItemEdges * kSubPerWarp);
+        const int rest = (deg - groups * kItemEdges * kSubPerWarp + kItemEdges - 1) / kItemEdges;
+        c.groups += groups; c.chunks += rest; c.slots += groups + rest; c.nlong++;
+    }
+};
+
+__host__ __device__ inline unsigned long long rest_key(int e0, int e1) {  // (length descending, first edge ascending)
+    return ((unsigned long long)(kItemEdges - (e1 - e0)) << 32) | (unsigned)e0;
+}
+
+struct WriteVisitor {
+    CutCounts off;      // exclusive offsets of this block
+    CutCounts tot;      // grand totals
+    int4 *items;        // merged-group items go straight to their final place
+    unsigned long long *rkeys;
+    int4 *ritems;       // whole-segment items [0, tot.whole), single chunks [tot.whole, tot.whole + tot.chunks)
+    int4 *fix;
+    int *nonempty_out;
+    int w = 0, g = 0, c = 0, sl = 0, l = 0, em = 0, ne = 0;
+    __host__ __device__ void empty(int s) { fix[tot.nlong + off.nempty + em++] = make_int4(s, 0, 0, 0); }
+    __host__ __device__ void nonempty(int s) { nonempty_out[off.nonempty + ne++] = s; }
+    __host__ __device__ void whole(int e0, int e1, int j) {
+        const int i = off.whole + w++;
+        ritems[i] = make_int4(e0, e1, off.nonempty + j, -1);
+        rkeys[i] = rest_key(e0, e1);
+    }
+    __host__ __device__ void long_seg(int s, int b, int e, int j) {
+        const int jj = off.nonempty + j, slot0 = off.slots + sl;
+        const int kGroup = kItemEdges * kSubPerWarp;
+        int cpos = b, k = 0;
+        for (; cpos + kGroup <= e; cpos += kGroup, k++) {
+            const int gi = off.groups + g++;
+            for (int t = 0; t < kSubPerWarp; t++)
+                items[(size_t)gi * kSubPerWarp + t] = make_int4(cpos + t * kItemEdges, cpos + (t + 1) * kItemEdges,
+                                                                jj | kMergedBit, t ? -2 : slot0 + k);
+        }
+        for (; cpos < e; cpos += kItemEdges, k++) {
+            const int i = tot.whole + off.chunks + c++;
+            const int e1 = cpos + kItemEdges < e ? cpos + kItemEdges : e;
+            ritems[i] = make_int4(cpos, e1, jj, slot0 + k);
+            rkeys[i] = rest_key(cpos, e1);
+        }
+        fix[off.nlong + l++] = make_int4(s, slot0, k, 0);
+        sl += k;
+    }
+};
+
+__global__ void cut_count_kernel(const int *__restrict__ ptr, int S, CutCounts *__restrict__ cnt, int nb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    CountVisitor v;
+    const int s0 = b * kCutBlock, s1 = min(S, s0 + kCutBlock);
+    if (s0 < s1) cut_walk_block(ptr, s0, s1, v);
+    cnt[b] = v.c;
+}
+
+__global__ void cut_write_kernel(const int *__restrict__ ptr, int S, const CutCounts *__restrict__ incl, int nb,
+                                 int4 *items, unsigned long long *rkeys, int4 *ritems, int4 *fix, int *nonempty) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    WriteVisitor v;
+    v.off = b ? incl[b - 1] : CutCounts{0, 0, 0, 0, 0, 0, 0};
+    v.tot = incl[nb - 1];
+    v.items = items; v.rkeys = rkeys; v.ritems = ritems; v.fix = fix; v.nonempty_out = nonempty;
+    const int s0 = b * kCutBlock, s1 = min(S, s0 + kCutBlock);
+    if (s0 < s1) cut_walk_block(ptr, s0, s1, v);
+}
+
+// sorted rest items -> behind the merged groups; pad to a multiple of 4; result counts for the launchers
+__global__ void cut_finalize_kernel(const CutCounts *__restrict__ incl, int nb, const int4 *__restrict__ sorted, int4 *items,
+                                    int *nonempty, int *counts) {
+    const CutCounts tot = incl[nb - 1];
+    const int G4 = tot.groups * kSubPerWarp, rest = tot.whole + tot.chunks;
+    const int padded = (rest + kSubPerWarp - 1) / kSubPerWarp * kSubPerWarp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x)
+        items[G4 + i] = i < rest ? sorted[i] : make_int4(0, 0, 0, -1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        nonempty[tot.nonempty] = 0;  // pad: the walker prefetches nonempty[j + 1]
+        counts[0] = G4 + padded;            // num_items
+        counts[1] = tot.nlong + tot.nempty;  // num_fix
+        counts[2] = tot.nlong;               // num_fix_long
+        counts[3] = tot.slots;               // num_slots
+        counts[4] = tot.nonempty + 1;        // entries of nonempty (incl. the pad)
+        counts[5] = tot.groups;
+        counts[6] = rest;
+        counts[7] = 0;
+    }
+}
+
+// Device cutter for one segment order: count -> scan -> write -> sort the non-group items -> finalize.  No host sync.
+int cut_items_device(const int *seg_ptr, int S, int64_t E, const WsLayout &L, char *ws, SegOrder &so, int *counts,
+                     cudaStream_t stream) {
+    const int nb = std::max(1, (S + kCutBlock - 1) / kCutBlock);
+    auto *cnt = reinterpret_cast<CutCounts *>(ws + L.cut_cnt);
+    auto *incl = reinterpret_cast<CutCounts *>(ws + L.cut_incl);
+    const int cap = (int)std::min<int64_t>(max_items(E, S), L.rest_cap);
+    cub::DoubleBuffer<unsigned long long> dk(reinterpret_cast<unsigned long long *>(ws + L.rkeys[0]),
+                                             reinterpret_cast<unsigned long long *>(ws + L.rkeys[1]));
+    cub::DoubleBuffer<int4> dv(reinterpret_cast<int4 *>(ws + L.ritems[0]), reinterpret_cast<int4 *>(ws + L.ritems[1]));
+    const int threads = 128, blocks = (nb + threads - 1) / threads;
+    cut_count_kernel<<<blocks, threads, 0, stream>>>(seg_ptr, S, cnt, nb);
+    CUDA_TRY(cudaGetLastError());
+    size_t temp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, temp_bytes, cnt, incl, CutSum(), nb, stream));
+    if (temp_bytes > L.cub_temp_bytes) { set_error("plan_build: internal scan scratch under-reserved"); return 4; }
+    temp_bytes = L.cub_temp_bytes;
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(ws + L.cub_temp, temp_bytes, cnt, incl, CutSum(), nb, stream));
+    CUDA_TRY(cudaMemsetAsync(dk.Current(), 0xff, (size_t)cap * 8, stream));  // unused entries sort to the end
+    cut_write_kernel<<<blocks, threads, 0, stream>>>(seg_ptr, S, incl, nb, so.items, dk.Current(), dv.Current(), so.fix,
+                                                     so.nonempty);
+    CUDA_TRY(cudaGetLastError());
+    temp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, cap, 0, 39, stream));
+    if (temp_bytes > L.cub_temp_bytes) { set_error("plan_build: internal sort scratch under-reserved"); return 4; }
+    temp_bytes = L.cub_temp_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, temp_bytes, dk, dv, cap, 0, 39, stream));  // 7 + 32 key bits
+    cut_finalize_kernel<<<std::max(1, std::min(cap / 256, 64)), 256, 0, stream>>>(incl, nb, dv.Current(), so.items,
+                                                                                  so.nonempty, counts);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
 
-size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layout(N, E, R, g_item_edges.load()).total; }
+size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R) { return make_layout(N, E, R).total; }
 
-int set_item_edges(int edges) {
-    if (edges != 16 && edges != 32 && edges != kItemEdges) return 1;
-    g_item_edges.store(edges);
-    return 0;
-}
-
-// Host-only access to the work-item cutter (pure CPU; used by the CPU test-suite to check its invariants).
+// Host mirror of the device cutter (same functions, run block after block): the CPU test-suite checks its invariants,
+// the GPU test-suite that the device kernels produce exactly this.
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
                    int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
                    int64_t nonempty_cap, int *num_nonempty) {
-    std::vector<int> ptr(seg_ptr, seg_ptr + num_seg + 1);
-    std::vector<int4> items, fix;
-    std::vector<int> nonempty;
-    int slots = 0, nlong = 0;
-    cut_items(ptr, items, nonempty, fix, slots, nlong, g_item_edges.load());
-    if ((int64_t)items.size() > items_cap || (int64_t)fix.size() > fix_cap || (int64_t)nonempty.size() > nonempty_cap) {
+    const int S = num_seg, nb = std::max(1, (S + kCutBlock - 1) / kCutBlock);
+    std::vector<CutCounts> incl(nb);
+    CutCounts run{0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < nb; b++) {
+        CountVisitor v;
+        const int s0 = b * kCutBlock, s1 = std::min(S, s0 + kCutBlock);
+        if (s0 < s1) cut_walk_block(seg_ptr, s0, s1, v);
+        run = cut_add(run, v.c);
+        incl[b] = run;
+    }
+    const CutCounts tot = incl[nb - 1];
+    const int rest = tot.whole + tot.chunks, G4 = tot.groups * kSubPerWarp;
+    const int padded = (rest + kSubPerWarp - 1) / kSubPerWarp * kSubPerWarp;
+    if (G4 + padded > items_cap || tot.nlong + tot.nempty > fix_cap || tot.nonempty + 1 > nonempty_cap) {
         set_error("cut_items_host: output capacity too small");
         return 1;
     }
-    if (!items.empty()) std::memcpy(items_out, items.data(), items.size() * sizeof(int4));
-    if (!fix.empty()) std::memcpy(fix_out, fix.data(), fix.size() * sizeof(int4));
-    if (!nonempty.empty()) std::memcpy(nonempty_out, nonempty.data(), nonempty.size() * sizeof(int));
-    *num_items = (int)items.size(); *num_fix = (int)fix.size(); *num_fix_long = nlong; *num_slots = slots;
-    *num_nonempty = (int)nonempty.size();
+    std::vector<int4> ritems(std::max(rest, 1));
+    std::vector<unsigned long long> rkeys(std::max(rest, 1));
+    for (int b = 0; b < nb; b++) {
+        WriteVisitor v;
+        v.off = b ? incl[b - 1] : CutCounts{0, 0, 0, 0, 0, 0, 0};
+        v.tot = tot;
+        v.items = reinterpret_cast<int4 *>(items_out); v.rkeys = rkeys.data(); v.ritems = ritems.data();
+        v.fix = reinterpret_cast<int4 *>(fix_out); v.nonempty_out = nonempty_out;
+        const int s0 = b * kCutBlock, s1 = std::min(S, s0 + kCutBlock);
+        if (s0 < s1) cut_walk_block(seg_ptr, s0, s1, v);
+    }
+    std::vector<int> order(rest);
+    for (int i = 0; i < rest; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return rkeys[a] < rkeys[b]; });  // keys are distinct
+    int4 *items = reinterpret_cast<int4 *>(items_out);
+    for (int i = 0; i < padded; i++) items[G4 + i] = i < rest ? ritems[order[i]] : make_int4(0, 0, 0, -1);
+    nonempty_out[tot.nonempty] = 0;
+    *num_items = G4 + padded; *num_fix = tot.nlong + tot.nempty; *num_fix_long = tot.nlong; *num_slots = tot.slots;
+    *num_nonempty = tot.nonempty + 1;
     return 0;
 }
 
@@ -218,8 +368,7 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         set_error("plan_build: num_node / num_edge / num_relation out of int32 range");
         return 1;
     }
-    const int item_edges = g_item_edges.load();  // one value for the size check and the cutter
-    const WsLayout L = make_layout(N, E, R, item_edges);
+    const WsLayout L = make_layout(N, E, R);
     if (workspace_bytes < L.total || (workspace == nullptr && L.total > 0)) {
         set_error("plan_build: workspace too small");
         return 1;
@@ -229,7 +378,7 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         return 1;
     }
     char *ws = static_cast<char *>(workspace);
-    auto *plan = new ultra_rspmm_plan();
+    std::unique_ptr<ultra_rspmm_plan> plan(new ultra_rspmm_plan());
     plan->N = N; plan->E = E; plan->R = R;
     CUDA_TRY(cudaGetDevice(&plan->device));
     {   // cudaGetDeviceProperties costs tens of ms per call; three attribute queries are microseconds
@@ -260,46 +409,34 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
     auto *valsA = reinterpret_cast<int *>(ws + L.valsA);
     auto *valsB = reinterpret_cast<int *>(ws + L.valsB);
     int *flags = reinterpret_cast<int *>(ws + L.flags);
+    int *counts = reinterpret_cast<int *>(ws + L.counts);
     plan->w_nonunit = flags + 2;
     plan->sched = flags + 4;
+    plan->counts = counts;
 
     const int threads = 256;
     const int blocks = (int)((E + threads - 1) / threads);
-    int h_flags[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemsetAsync(flags, 0, 64, stream));
     if (E > 0) {
         validate_kernel<<<blocks, threads, 0, stream>>>(edge_index, edge_type, N, E, R, flags);
         CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaMemcpyAsync(h_flags, flags, 16, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (h_flags[0]) {
-        delete plan;
-        set_error("plan_build: edge_index / edge_type value out of range [0, num_node) / [0, num_relation)");
-        return 3;
-    }
-    plan->input_sorted = h_flags[1] ? 0 : 1;
-
-    std::vector<int> h_ptr;
-    std::vector<int4> items, fix;
-    std::vector<int> nonempty;
+    // Everything below is enqueued without looking at the flags: if an index is out of range the keys are garbage but
+    // every kernel stays inside its buffers (indices are only used as sort keys / stored values until forward runs),
+    // and the plan is rejected after the ONE synchronisation at the end.
     for (int o = 0; o < 3; o++) {
         SegOrder &so = plan->ord[o];
         const int sec_bits = bits_for(std::max<int64_t>(N, 2));
         const int pri_bits = bits_for(std::max<int64_t>(S[o], 2));
         if (E > 0) {
-            make_keys_kernel<<<blocks, threads, 0, stream>>>(o, edge_index, edge_type, E, sec_bits, keysA, valsA);
+            make_keys_kernel<<<blocks, threads, 0, stream>>>(o, edge_index, edge_type, E, N, R, sec_bits, keysA, valsA);
             CUDA_TRY(cudaGetLastError());
             cub::DoubleBuffer<unsigned long long> dk(keysA, keysB);
             cub::DoubleBuffer<int> dv(valsA, valsB);
             size_t temp_bytes = 0;
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int)E, 0, sec_bits + pri_bits,
                                                      stream));
-            if (temp_bytes > L.cub_temp_bytes) {
-                delete plan;
-                set_error("plan_build: internal sort scratch under-reserved");
-                return 4;
-            }
+            if (temp_bytes > L.cub_temp_bytes) { set_error("plan_build: internal sort scratch under-reserved"); return 4; }
             temp_bytes = L.cub_temp_bytes;
             CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, temp_bytes, dk, dv, (int)E, 0,
                                                      sec_bits + pri_bits, stream));
@@ -310,25 +447,25 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         } else {
             CUDA_TRY(cudaMemsetAsync(so.seg_ptr, 0, (size_t)(S[o] + 1) * 4, stream));
         }
-        h_ptr.resize((size_t)S[o] + 1);
-        CUDA_TRY(cudaMemcpyAsync(h_ptr.data(), so.seg_ptr, (size_t)(S[o] + 1) * 4, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        cut_items(h_ptr, items, nonempty, fix, so.num_slots, so.num_fix_long, item_edges);
-        if ((int64_t)items.size() > max_items(E, item_edges)) {
-            delete plan;
-            set_error("plan_build: item bound exceeded");
-            return 4;
-        }
-        so.num_items = (int)items.size();
-        so.num_fix = (int)fix.size();
-        if (!items.empty())
-            CUDA_TRY(cudaMemcpyAsync(so.items, items.data(), items.size() * 16, cudaMemcpyHostToDevice, stream));
-        if (!fix.empty())
-            CUDA_TRY(cudaMemcpyAsync(so.fix, fix.data(), fix.size() * 16, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(so.nonempty, nonempty.data(), nonempty.size() * 4, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));  // host vectors are reused by the next order
+        if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream)) return rc;
     }
-    *out = plan;
+    // the one synchronisation of a plan build: validation flags + the three orders' item / fix / slot counts
+    int h[4 + 3 * kPlanCounts];
+    CUDA_TRY(cudaMemcpyAsync(h, flags, 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(h + 4, counts, 3 * kPlanCounts * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h[0]) {
+        set_error("plan_build: edge_index / edge_type value out of range [0, num_node) / [0, num_relation)");
+        return 3;
+    }
+    plan->input_sorted = h[1] ? 0 : 1;
+    for (int o = 0; o < 3; o++) {
+        SegOrder &so = plan->ord[o];
+        const int *c = h + 4 + o * kPlanCounts;
+        so.num_items = c[0]; so.num_fix = c[1]; so.num_fix_long = c[2]; so.num_slots = c[3];
+        if ((int64_t)so.num_items > max_items(E, S[o])) { set_error("plan_build: item bound exceeded"); return 4; }
+    }
+    *out = plan.release();
     return 0;
 }
 

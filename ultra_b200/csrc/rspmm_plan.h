@@ -33,6 +33,7 @@ struct ultra_rspmm_plan {
     ultra::SegOrder ord[3];  // FWD (by row), BWD_IN (by col), BWD_REL (by relation)
     int *row_of_edge = nullptr;  // (E) row of each edge in FWD order (weight_grad kernel)
     int *w_nonunit = nullptr;    // device flag: some bound weight != 1
+    int *counts = nullptr;       // (3 orders x 8) device copy of {num_items, num_fix, num_fix_long, num_slots, ...}
     int *sched = nullptr;        // (3 orders x 2) device work-queue tickets {next block, CTAs done}; self-resetting
     bool unit_weight = true;
     int w_dtype = -1;
@@ -48,8 +49,6 @@ struct ultra_rspmm_plan {
 namespace ultra {
 void set_error(const std::string &msg);
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
-// tunable "item_edges": 64 (default), 32 or 16 edges per work item for plans built afterwards; returns 1 on a bad value
-int set_item_edges(int edges);
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
                    int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
                    int64_t nonempty_cap, int *num_nonempty);
