@@ -145,3 +145,25 @@ def test_merge_parallel_edges_preserves_the_sum_aggregate():
     torch.testing.assert_close(got, exp, rtol=1e-5, atol=1e-5 * float(exp.abs().max()))
     dup_ei, dup_et = torch.cat([ei, ei[:, :1]], 1), torch.cat([et, et[:1]])
     assert merge_parallel_edges(dup_ei, dup_et, R) is None
+
+
+def test_easy_edge_mask_matches_brute_force():
+    """UltraNBFNet.easy_edge_mask == remove_easy_edges' mask (/root/reference/ultra/base_nbfnet.py:54-77), by brute force."""
+    from ultra_b200.nbfnet import UltraNBFNet
+    g = torch.Generator().manual_seed(13)
+    N, R, E = 40, 6, 500  # R counts inverse relations: r + R/2 is the inverse of r
+    ei = torch.randint(0, N, (2, E), generator=g)
+    et = torch.randint(0, R, (E,), generator=g)
+    pick = torch.randint(0, E, (8,), generator=g)
+    pick = pick[et[pick] < R // 2]
+    h, t, r = ei[0, pick], ei[1, pick], et[pick]
+    for one_hop in (False, True):
+        mask = UltraNBFNet.easy_edge_mask(ei, et, N, R, h, t, r, remove_one_hop=one_hop)
+        batch = set()
+        for a, b, c in zip(h.tolist(), t.tolist(), r.tolist()):
+            batch.add((a, b, c)); batch.add((b, a, c + R // 2))
+        pairs = {(a, b) for a, b, _ in batch}
+        exp = [((u, v) not in pairs) if one_hop else ((u, v, w) not in batch)
+               for u, v, w in zip(ei[0].tolist(), ei[1].tolist(), et.tolist())]
+        assert mask.tolist() == exp
+        assert not mask[pick].any()

@@ -248,3 +248,24 @@ def test_pna_one_pass_equals_four_calls(cuda_device, mul, dtype, D):
     for name, s_, a in (("sum", "add", outs[0]), ("max", "max", outs[2]), ("min", "min", outs[3])):
         exp = oracle_all(s_, mul, ei.cpu(), et.cpu(), w.cpu(), rel, x)
         (assert_close_ref if s_ == "add" else assert_equal_values)(a.detach(), exp, name + " vs oracle")
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+def test_zero_one_weights_remove_edges_for_sum(cuda_device, mul):
+    """The incremental alternative to re-planning a masked graph (GraphPlan.edge_mask_weight): for the sum aggregate a
+    0/1 edge weight on the BASE graph's plan equals rspmm on the physically filtered edge list (forward and grads)."""
+    from ultra_b200.rspmm import generalized_rspmm
+    from ultra_b200.plan import plan_cache
+    ei, et, w, rel, x, og = random_case(61, 500, 20000, 7, 128, hub=3000, unit_weight=True)
+    g = torch.Generator().manual_seed(62)
+    keep = torch.rand(ei.shape[1], generator=g) > 0.1
+    d = cuda_device
+    eid, etd = ei.to(d), et.to(d)
+    plan = plan_cache.get(eid, etd, 500, 7)
+    relg, xg = rel.to(d).requires_grad_(), x.to(d).requires_grad_()
+    out = generalized_rspmm(eid, etd, plan.edge_mask_weight(keep.to(d)), relg, xg, sum="add", mul=mul)
+    out.backward(og.to(d))
+    e_out, _, e_rg, e_ig = oracle_all("add", mul, ei[:, keep], et[keep], torch.ones(int(keep.sum())), rel, x, og)
+    assert_close_ref(out.detach(), e_out, "masked forward")
+    assert_close_ref(relg.grad, e_rg, "masked relation_grad")
+    assert_close_ref(xg.grad, e_ig, "masked input_grad")

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--peak", type=float, default=6583.2)
     ap.add_argument("--l2-percent", type=int, default=0)
     ap.add_argument("--sm-limit", type=int, default=0)
+    ap.add_argument("--mask-frac", type=float, default=0.0,
+                    help="bind a 0/1 edge weight that removes this fraction of the edges (the weighted kernel path)")
     args = ap.parse_args()
     d = torch.device("cuda:0")
     lib = _capi.lib()
@@ -54,6 +56,11 @@ def main():
         plan = GraphPlan(ei.to(d), et.to(d), N, R)
         if args.sm_limit:
             plan.set_sm_limit(args.sm_limit)
+        if args.mask_frac > 0:
+            keep = torch.rand(E, device=d, generator=g) >= args.mask_frac
+            wmask = plan.edge_mask_weight(keep)
+            med, best = time_fn(lambda: (plan.invalidate_weight(), plan.bind_weight(wmask)))
+            print(json.dumps({"weight_bind_ms_med": round(med, 4), "removed_edges": int((~keep).sum())}))
         scratch = plan.scratch(D, torch.float32)
         deg = torch.bincount(ei[0], minlength=N)
         print(json.dumps({"alpha": alpha, "N": N, "E": E, "R": R, "D": D, "max_deg": int(deg.max()),

@@ -100,8 +100,26 @@ class UltraNBFNet(nn.Module):
         boundary.scatter_add_(1, index.view(-1, 1, 1).expand(-1, 1, value.shape[-1]), value.unsqueeze(1))
         return boundary
 
-    def _bellmanford(self, layers, boundary, query, edge_index, edge_type, num_node, relations=None, hook=None):
-        w = self._unit_weight(edge_index.shape[1], boundary)
+    @staticmethod
+    def easy_edge_mask(edge_index, edge_type, num_node, num_relation, h_index, t_index, r_index, remove_one_hop=False):
+        """keep-mask of remove_easy_edges (/root/reference/ultra/base_nbfnet.py:54-77): False for every edge
+        (h, t, r) / (t, h, r + R/2) of the training batch (or every edge between the pairs when remove_one_hop).  The
+        reference's edge_match (tasks.py:7-39) is a hashing + bucketize search; an integer-key `isin` gives the same set.
+        Returns a bool (E,) tensor: feed it to the forward as `edge_mask` - for the sum aggregate it is applied as a 0/1
+        edge weight on the base graph's plan, nothing is re-sorted (see GraphPlan.edge_mask_weight)."""
+        h = torch.cat([h_index.flatten(), t_index.flatten()])
+        t = torch.cat([t_index.flatten(), h_index.flatten()])
+        key = edge_index[0] * num_node + edge_index[1]
+        easy = h * num_node + t
+        if not remove_one_hop:
+            r = torch.cat([r_index.flatten(), r_index.flatten() + num_relation // 2])
+            key = key * num_relation + edge_type
+            easy = easy * num_relation + r
+        return ~torch.isin(key, easy)
+
+    def _bellmanford(self, layers, boundary, query, edge_index, edge_type, num_node, relations=None, hook=None,
+                     edge_weight=None):
+        w = self._unit_weight(edge_index.shape[1], boundary) if edge_weight is None else edge_weight
         x = boundary
         for i, layer in enumerate(layers):
             residual = self.short_cut and layer.output_dim == x.shape[-1]
@@ -132,8 +150,9 @@ class UltraNBFNet(nn.Module):
         relations = [combos @ layer.relation.weight for layer in layers]
         return self._bellmanford(layers, boundary, ones, mei, met, num_relation, relations)
 
-    def entity_states(self, edge_index, edge_type, num_node, rel_repr, h_index, r_index, hook=None):
-        """EntityNBFNet.bellmanford (models.py:131-175) -> (h (B, N, d) last hidden, query (B, d))."""
+    def entity_states(self, edge_index, edge_type, num_node, rel_repr, h_index, r_index, hook=None, edge_mask=None):
+        """EntityNBFNet.bellmanford (models.py:131-175) -> (h (B, N, d) last hidden, query (B, d)).
+        edge_mask (bool (E,), optional): edges to KEEP this step (training: easy_edge_mask)."""
         layers = self.entity_model.layers
         query = rel_repr[torch.arange(len(r_index), device=r_index.device), r_index]
         projections = [layer.relation_projection for layer in layers]
@@ -142,7 +161,12 @@ class UltraNBFNet(nn.Module):
         else:
             relations = [p(rel_repr) for p in projections]
         boundary = self._boundary(h_index, query, num_node)
-        return self._bellmanford(layers, boundary, query, edge_index, edge_type, num_node, relations, hook), query
+        weight = None
+        if edge_mask is not None:
+            if layers[0].aggregate_func != "sum":
+                raise ValueError("edge_mask is applied as a 0/1 edge weight, which is only an edge removal for `sum`")
+            weight = edge_mask.to(boundary.dtype)
+        return self._bellmanford(layers, boundary, query, edge_index, edge_type, num_node, relations, hook, weight), query
 
     def score(self, h, query, t_index):
         """models.py:166-170,202-208 for explicit tails t_index (B, K): gather cat[h, query] rows, MLP -> (B, K)."""
@@ -168,11 +192,12 @@ class UltraNBFNet(nn.Module):
         return out
 
     # ---- Ultra.forward -----------------------------------------------------------------------------------------------
-    def forward(self, rel_graph, graph, h_index, r_index, t_index=None):
+    def forward(self, rel_graph, graph, h_index, r_index, t_index=None, edge_mask=None):
         """rel_graph / graph: (edge_index, edge_type, num_node) of the relation graph / the entity graph (already in tail-
-        prediction form: one (h, r) query per head).  Returns scores (B, K) for t_index (B, K), or (B, N) for all tails."""
+        prediction form: one (h, r) query per head).  Returns scores (B, K) for t_index (B, K), or (B, N) for all tails.
+        edge_mask: bool (E,) keep-mask over the entity graph's edges for this step (training, see easy_edge_mask)."""
         rel_repr = self.relation_representations(rel_graph[0], rel_graph[1], rel_graph[2], r_index)
-        h, query = self.entity_states(graph[0], graph[1], graph[2], rel_repr, h_index, r_index)
+        h, query = self.entity_states(graph[0], graph[1], graph[2], rel_repr, h_index, r_index, edge_mask=edge_mask)
         return self.score_all(h, query) if t_index is None else self.score(h, query, t_index)
 
 
