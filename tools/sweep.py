@@ -30,6 +30,23 @@ def time_fn(fn, warmup=2, iters=5):
     return ts[len(ts) // 2]
 
 
+def parity_first_head(ei, et, rel, x, out, cols=64, chunk=4_000_000):
+    """Same-run correctness of the timed forward: the first `cols` columns against the dense PyTorch formula
+    out[i] = sum_{e: row_e = i} rel[type_e] * x[col_e] accumulated in fp64 on the GPU,
+    north-star tolerance 1e-5 relative to max|ref| (+ the fp32 reference's own rounding on very long rows is not an
+    issue here because the reference side is fp64)."""
+    N = x.shape[0]
+    ref = torch.zeros(N, cols, dtype=torch.float64, device=x.device)
+    r64, x64 = rel[:, :cols].double(), x[:, :cols].double()
+    for lo in range(0, ei.shape[1], chunk):
+        sl = slice(lo, lo + chunk)
+        ref.index_add_(0, ei[0, sl], r64[et[sl]] * x64[ei[1, sl]])
+    scale = float(ref.abs().max())
+    err = float((out[:, :cols].double() - ref).abs().max())
+    return {"cols": cols, "max_abs_err": err, "max_abs_ref": scale, "rel_to_max": err / scale if scale else 0.0,
+            "ok": bool(err <= 1e-5 * scale)}
+
+
 def measure(name, ei, et, N, R, D, peak, bwd=True, extra=None):
     d = ei.device
     lib = _capi.lib()
@@ -46,11 +63,12 @@ def measure(name, ei, et, N, R, D, peak, bwd=True, extra=None):
                                      scratch.data_ptr(), scratch.numel(), _stream_ptr(d))
         assert rc == 0, lib.ultra_rspmm_last_error()
     ms = time_fn(fwd)
+    parity = parity_first_head(ei, et, rel, x, out)
     ba, bm = algorithmic_bytes(N, E, R, D), compulsory_bytes(N, E, R, D)
     rec = {"config": name, "N": N, "E": E, "R": R, "D": D, "fwd_ms": round(ms, 4),
            "Medges_s": round(E / ms / 1e3, 1), "alg_GBs": round(ba / ms / 1e6, 1),
            "frac_alg": round(ba / ms / 1e6 / peak, 3), "frac_compulsory": round(bm / ms / 1e6 / peak, 3),
-           "max_deg": int(torch.bincount(ei[0], minlength=N).max())}
+           "max_deg": int(torch.bincount(ei[0], minlength=N).max()), "parity": parity}
     if bwd:
         og = torch.randn_like(x)
         ig, rg = torch.empty_like(x), torch.empty_like(rel)
@@ -69,7 +87,7 @@ def measure(name, ei, et, N, R, D, peak, bwd=True, extra=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default="gpurun_out/r01_sweep.jsonl")
+    ap.add_argument("--out", default="gpurun_out/r02_sweep_out.jsonl")
     ap.add_argument("--peak", type=float, default=6583.2)
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
