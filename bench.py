@@ -82,7 +82,10 @@ def l2_gather(counters, ms):
         return None
     achieved = counters["l2_to_l1_bytes"] / (ms * 1e-3) / 1e9
     return {"achieved": achieved, "peak": L2_GATHER_PEAK_GBS, "unit": "GB/s", "frac": achieved / L2_GATHER_PEAK_GBS,
-            "bytes_per_launch": counters["l2_to_l1_bytes"], "l1_hit_rate": counters.get("l1_hit_rate")}
+            "bytes_per_launch": counters["l2_to_l1_bytes"], "l1_hit_rate": counters.get("l1_hit_rate"),
+            "peak_note": "rate of the 4-loads-in-flight gather microbench, NOT a hard ceiling: the two-gather backward pass "
+                         "of the same template sustains 8.5 TB/s (profiles/roofline_traffic.json backward_rel); the forward "
+                         "pass is short of bytes in flight (DESIGN.md 3.1)"}
 
 
 class ClockSampler:

@@ -438,3 +438,73 @@ def test_training_layer_uses_fused_epilogue_and_matches_restatement(cuda_device)
         GeneralizedRelationalConv.fuse = True
     for a, b in zip(*results):
         torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4 * max(float(b.abs().max()), 1.0))
+
+
+def test_training_step_with_edge_mask_is_cuda_graph_capturable(cuda_device):
+    """A training step of an entity layer - forward + backward, with this step's easy edges removed - captured as ONE
+    CUDA graph and replayed with a different mask (the reference re-sorts the masked edge list inside
+    every rspmm call and synchronises the host, rspmm.py:15-17,174-178 - nothing of that can be captured).  The mask
+    is a 0/1 edge weight on the base graph's plan (GraphPlan.edge_mask_weight); the captured weight bind re-permutes it
+    on every replay.  Checked against an eager step on the physically filtered edge list."""
+    from ultra_b200.layer import GeneralizedRelationalConv
+    from ultra_b200.plan import plan_cache
+    torch.manual_seed(23)
+    dev = cuda_device
+    B, N, R, d, E = 3, 300, 8, 64, 5000
+    layer = GeneralizedRelationalConv(d, d, R, d, "distmult", "sum", layer_norm=True, project_relations=True).to(dev)
+    ei = torch.randint(0, N, (2, E), device=dev)
+    et = torch.randint(0, R, (E,), device=dev)
+    query = torch.randn(B, d, device=dev)
+    bd = torch.randn(B, N, d, device=dev)
+    gout = torch.randn(B, N, d, device=dev)
+    s_x = torch.randn(B, N, d, device=dev).requires_grad_()
+    s_rel = torch.randn(B, R, d, device=dev).requires_grad_()
+    s_w = torch.ones(E, device=dev)  # static weight buffer: this step's keep-mask as floats
+    layer.relation = s_rel
+    params = list(layer.parameters())
+
+    def step(edge_index, edge_type, weight):
+        out = layer(s_x, query, bd, edge_index, edge_type, (N, N), weight, shortcut=True)
+        out.backward(gout)
+        return out
+
+    def zero():
+        for t in [s_x, s_rel] + params:
+            t.grad = None
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step(ei, et, s_w)
+            zero()
+    torch.cuda.current_stream().wait_stream(side)
+    plan = plan_cache.get(ei, et, N, R)
+    plan.invalidate_weight()  # so that the weight bind (permute kernel) is part of the captured graph
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_out = step(ei, et, s_w)
+    g_grads = [s_x.grad, s_rel.grad] + [p.grad for p in params]
+    for seed in (1, 2):
+        keep = torch.rand(E, device=dev, generator=torch.Generator(device=dev).manual_seed(seed)) > 0.05
+        with torch.no_grad():
+            s_w.copy_(plan.edge_mask_weight(keep))
+        graph.replay()
+        got = [g_out.detach().clone()] + [g.clone() for g in g_grads]
+        plan.invalidate_weight()
+        # eager reference on the filtered edge list (a different plan, unit weights)
+        zero_ref = [t.grad for t in [s_x, s_rel] + params]  # the graph's static grad tensors: keep them, use fresh leaves
+        x2, rel2 = s_x.detach().clone().requires_grad_(), s_rel.detach().clone().requires_grad_()
+        layer.relation = rel2
+        for p in params:
+            p.grad = None
+        out2 = layer(x2, query, bd, ei[:, keep].contiguous(), et[keep].contiguous(), (N, N),
+                     torch.ones(int(keep.sum()), device=dev), shortcut=True)
+        out2.backward(gout)
+        exp = [out2.detach(), x2.grad, rel2.grad] + [p.grad for p in params]
+        for a, b in zip(got, exp):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4 * max(float(b.abs().max()), 1.0))
+        # restore the static state for the next replay
+        layer.relation = s_rel
+        for p, g in zip([s_x, s_rel] + params, zero_ref):
+            p.grad = g

@@ -533,13 +533,16 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
     // CTA that drew short items simply takes the next block (static round-robin left a ~1/waves tail: 15 % at 32 heads
     // per GPU, where a CTA only sees ~5 blocks).  The order in which tiles are visited - what keeps the gathered tiles
     // L2-resident - is unchanged.  Results do not depend on which CTA computes a unit.
+    // The next ticket is drawn at the START of a block and published at its end, so the atomic's round trip (~1 us,
+    // 19 blocks per CTA at C2 = 1 % of the call when it was exposed) overlaps the block's work.
     __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
+    __syncthreads();
     for (;;) {
-        __syncthreads();  // everyone has read the previous ticket
-        if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
-        __syncthreads();
         const long long blk = s_ticket;
         if (blk * p.run >= p.total_units) break;
+        int next_ticket = 0;
+        if (threadIdx.x == 0) next_ticket = atomicAdd(p.sched, 1);  // consumed only after the block (no stall here)
         for (int uu = 0; uu < p.run; uu++) {
             const long long unit = blk * p.run + uu;
             if (unit >= p.total_units) break;
@@ -580,6 +583,9 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
                 if (wi < p.num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, meta_s_addr, use_w);
             }
         }
+        __syncthreads();  // every thread has read this block's ticket
+        if (threadIdx.x == 0) s_ticket = next_ticket;
+        __syncthreads();
     }
     // the last CTA to leave resets the queue for the next launch on this plan (launches of one plan are stream-ordered)
     if (threadIdx.x == 0) {
