@@ -160,11 +160,13 @@ def test_plan_cache_reused_across_layers(cuda_device):
     assert plan_cache.misses == m0 + 2
 
 
+@pytest.mark.parametrize("D", [1100, 2852], ids=["3_slabs", "6_slabs_ragged"])
 @pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "add")])
-def test_host_tensors_are_staged_through_gpu(cuda_device, sum, mul):
+def test_host_tensors_are_staged_through_gpu(cuda_device, sum, mul, D):
     """CPU tensors in -> CPU tensors out (reference dispatches on input.device.type, rspmm.py:19-22); the work
-    runs on the GPU in pipelined column slabs (ultra_rspmm_forward_host)."""
-    ei, et, w, rel, x, og = random_case(46, 300, 5000, 9, 1100, hub=900)  # 1100 cols -> 3 slabs of 512
+    runs on the GPU in pipelined column slabs (ultra_rspmm_forward_host).  1100 columns -> 3 slabs of 512; 2852
+    columns -> 6 slabs, the last one ragged (both staging buffers are reused twice)."""
+    ei, et, w, rel, x, og = random_case(46, 300, 5000, 9, D, hub=900)
     ours = run_ours(sum, mul, ei, et, w, rel.pin_memory(), x.pin_memory(), og, device="cpu")
     assert ours[0].device.type == "cpu"
     check_against(sum, mul, ours, oracle_all(sum, mul, ei, et, w, rel, x, og))
