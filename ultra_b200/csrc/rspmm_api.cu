@@ -34,7 +34,8 @@ static_assert(kCtasPerSm != 2 || kCtaThreads != 512 || kSlabSmemLimit == 78 * 10
 // process-wide launch tunables (ultra_rspmm_set_tunable); the SM reservation is per plan (ultra_rspmm_plan_set_sm_limit)
 std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
 std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy
-std::atomic<int> g_bwd_fused_relgrad{0}; // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
+std::atomic<int> g_bwd_fused_relgrad{0};
+std::atomic<int> g_smem_tiles{2};       // experiment knob: highest SM mode allowed (2 all, 1 relation tile only, 0 none) // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
 
 template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
     if (D % VecN<T>::value != 0) return false;
@@ -137,6 +138,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         int sm_mode = 0;
         if (rel_bytes + g1_bytes <= kSlabSmemLimit) sm_mode = 2;
         else if (Nd::rel && rel_bytes <= kSlabSmemLimit) sm_mode = 1;
+        sm_mode = std::min(sm_mode, g_smem_tiles.load());
         auto launch = [&](auto kern, size_t smem) -> int {
             if (smem > 48 * 1024) {  // opt-in above 48 KB; cudaFuncSetAttribute is cheap and idempotent
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -313,8 +315,9 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     const std::string n(name);
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
+    if (n == "smem_tiles") { g_smem_tiles.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad)");
+    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, smem_tiles)");
     return 1;
 }
 
