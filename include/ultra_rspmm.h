@@ -68,7 +68,8 @@ int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out,
 /*
  * Test hook: copy one array of a built plan to the host (synchronous).  order: 0 by row, 1 by col, 2 by relation;
  * what: 0 items (int4 x plan_info items), 1 fix list (int4), 2 non-empty segment ids (num_seg + 1 ints, entries past
- * the count are unspecified), 3 segment pointer (num_seg + 1 ints).  The GPU test-suite compares these with the host
+ * the count are unspecified), 3 segment pointer (num_seg + 1 ints), 4 the device-side counts (8 ints: items, fix entries,
+ * long-segment fix entries, slots, non-empty entries, merged groups, other items, edges).  The GPU test-suite compares these with the host
  * mirror (ultra_rspmm_debug_cut_items); not used by the product path.
  */
 int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int what, void *host_out, int64_t cap_bytes);
@@ -92,6 +93,21 @@ size_t ultra_rspmm_plan_workspace_bytes(int64_t num_node, int64_t num_edge, int6
 int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_index, const int64_t *edge_type,
                            int64_t num_node, int64_t num_edge, int64_t num_relation, void *workspace,
                            size_t workspace_bytes, void *stream);
+
+/*
+ * Edge masks - the incremental plan for the training loop's per-step edge removal (remove_easy_edges,
+ * /root/reference/ultra/base_nbfnet.py:54-77; the reference indexes the edge tensors and then re-sorts the result inside
+ * every rspmm call, /root/reference/ultra/rspmm/rspmm.py:174-178).  keep_mask: device bytes, one per edge of the BASE
+ * graph in the caller's edge order (a torch.bool tensor), non-zero = keep.  The plan is re-cut for that sub-graph entirely
+ * on the device - removing edges keeps every order sorted, so: scan, compact, gather the new segment pointers, work-item
+ * cutter; no sort - and WITHOUT a host synchronisation (CUDA-graph capturable): the host keeps upper bounds for grid and
+ * scratch sizing, the kernels read the exact counts from device memory.  Forward / backward afterwards compute exactly
+ * what a plan built from the filtered edge list would (same cutter on the same segment pointers: bit-identical).
+ * Edge weights and weight_grad keep the base graph's length and order (entries of removed edges are ignored / zero).
+ * ultra_rspmm_scratch_bytes grows while a mask is applied (split-row partials are bounded, not counted).
+ * keep_mask == NULL restores the base graph.
+ */
+int ultra_rspmm_plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep_mask, void *stream);
 
 void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan);
 

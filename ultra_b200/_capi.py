@@ -23,6 +23,7 @@ SYMBOLS = {
     "ultra_rspmm_plan_debug_read": (_int, [_vp, _int, _int, _vp, _i64]),
     "ultra_rspmm_plan_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ultra_rspmm_plan_build": (_int, [ctypes.POINTER(_vp), _vp, _vp, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "ultra_rspmm_plan_apply_mask": (_int, [_vp, _vp, _vp]),
     "ultra_rspmm_plan_destroy": (None, [_vp]),
     "ultra_rspmm_plan_input_sorted": (_int, [_vp]),
     "ultra_rspmm_plan_info": (_i64, [_vp, _int]),

@@ -99,7 +99,8 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
 
     SegParams<T> p;
     p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.sched = plan->sched + 2 * ORD; p.nonempty = so.nonempty; p.items = so.items;
-    p.num_warp_items = so.num_items / kSubPerWarp;
+    p.counts = so.counts;
+    const int ub_warp_items = so.num_items / kSubPerWarp;  // exact for the base graph, an upper bound under an edge mask
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
     p.dst = dst; p.rgrad = rgrad; p.partial = scratch; p.boundary = boundary; p.lay = lay;
     p.dst_plane = (long long)plan->ord[ORD].num_seg * D;          // S_PNA: (4, N, D) outputs
@@ -107,29 +108,29 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     p.D = (int)D; p.R = (int)plan->R; p.N = (int)plan->N;
     p.num_tiles = (int)((D + TILE - 1) / TILE);
 
-    if (p.num_warp_items > 0) {
+    if (ub_warp_items > 0) {
         const int sm_limit = plan->sm_limit;
         const int ctas = ((sm_limit > 0 && sm_limit < plan->sm_count) ? sm_limit : plan->sm_count) * kCtasPerSm;
         // items per warp per unit: 2 when that still leaves every CTA several units
         int ipw = 2;
-        auto units_per_tile = [&](int k) { return (p.num_warp_items + kCtaWarps * k - 1) / (kCtaWarps * k); };
+        auto units_per_tile = [&](int k) { return (ub_warp_items + kCtaWarps * k - 1) / (kCtaWarps * k); };
         if ((long long)units_per_tile(ipw) * p.num_tiles < 4LL * ctas) ipw = 1;
         p.items_per_warp = ipw;
-        p.units_per_tile = units_per_tile(ipw);
-        p.total_units = (long long)p.units_per_tile * p.num_tiles;
+        const int ub_units_per_tile = units_per_tile(ipw);  // the kernel recomputes both from the device-side count
+        const long long ub_total_units = (long long)ub_units_per_tile * p.num_tiles;
         // tile-major walk: each CTA takes `run` consecutive units, so ~ctas*run/units_per_tile tiles are in
         // flight; keep their gathered footprint (segments' source rows x 128 B) within a fraction of L2.
         const size_t l2_budget = (plan->l2_bytes ? plan->l2_bytes : (size_t)96 << 20) / 100 * (size_t)g_l2_percent.load();
         const size_t rows_gathered = (size_t)std::max<int64_t>(plan->N, 1) * Nd::gathers;  // matrices gathered from
         const double tiles_in_flight = std::max(1.0, (double)l2_budget / ((double)rows_gathered * kTileBytes));
-        long long run = (long long)(tiles_in_flight * p.units_per_tile / ctas);
-        run = std::max<long long>(1, std::min<long long>(run, p.units_per_tile));
+        long long run = (long long)(tiles_in_flight * ub_units_per_tile / ctas);
+        run = std::max<long long>(1, std::min<long long>(run, ub_units_per_tile));
         // ... but never so long that CTAs go idle: keep >= 4 blocks of `run` units per CTA when the work allows it
         // (small graphs have huge tiles_in_flight; without this cap each CTA would own a whole tile and a
         // 32-tile problem would occupy 32 of 296 CTAs)
-        run = std::max<long long>(1, std::min<long long>(run, p.total_units / (4LL * ctas)));
+        run = std::max<long long>(1, std::min<long long>(run, ub_total_units / (4LL * ctas)));
         p.run = (int)run;
-        const long long nblk = (p.total_units + p.run - 1) / p.run;
+        const long long nblk = (ub_total_units + p.run - 1) / p.run;
         const int grid = (int)std::min<long long>(nblk, ctas);
 
         // shared-memory residency: relation tile (R x 128 B) and, for small graphs, the gathered matrix' tile too
@@ -155,7 +156,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         CUDA_TRY(cudaGetLastError());
     }
     const int ncc = (int)((D + 32 * V - 1) / (32 * V));
-    const int num_empty = so.num_fix - so.num_fix_long;
+    const int num_empty = so.num_fix - so.num_fix_long;  // upper bounds under an edge mask
     // one fold + one identity fill per accumulator plane (1, or 4 for S_PNA: sum, sum of squares, max, min)
     auto fix_plane = [&](auto red_tag, int a) -> int {
         constexpr int RED = decltype(red_tag)::value;
@@ -163,14 +164,14 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
         const T *part_a = scratch + (size_t)a * p.partial_plane;
         if (so.num_fix_long > 0) {
             fold_partials_kernel<T, RED><<<so.num_fix_long * ncc, 256, 0, stream>>>(
-                so.fix, so.num_fix_long, part_a, dst_a, boundary, (int)D, lay, dst_grp_bytes);
+                so.fix, so.counts, part_a, dst_a, boundary, (int)D, lay, dst_grp_bytes, ncc);
             CUDA_TRY(cudaGetLastError());
         }
         if (num_empty > 0) {
             const long long warps = (long long)num_empty * ncc;
-            const int blocks = (int)((warps * 32 + 255) / 256);
-            fill_identity_kernel<T, RED><<<blocks, 256, 0, stream>>>(so.fix + so.num_fix_long, num_empty, dst_a,
-                                                                     boundary, (int)D, lay, dst_grp_bytes);
+            const int blocks = (int)std::min<long long>((warps * 32 + 255) / 256, (long long)plan->sm_count * 32);
+            fill_identity_kernel<T, RED><<<blocks, 256, 0, stream>>>(so.fix, so.counts, dst_a, boundary, (int)D, lay,
+                                                                     dst_grp_bytes);
             CUDA_TRY(cudaGetLastError());
         }
         return 0;
@@ -222,10 +223,12 @@ int backward_t(const ultra_rspmm_plan *plan, const void *relation, const void *i
     if (wgrad != nullptr && plan->E > 0) {
         const SegOrder &so = plan->ord[FWD];
         const T *w = plan->unit_weight ? nullptr : static_cast<const T *>(so.w);
+        if (plan->masked)  // removed edges receive no gradient: their (base-order) entries are zero
+            CUDA_TRY(cudaMemsetAsync(wgrad, 0, (size_t)plan->E * sizeof(T), stream));
         const long long threads = (long long)plan->E * 32;
         wgrad_kernel<T, SUM, MUL><<<(int)((threads + 255) / 256), 256, 0, stream>>>(
             so.meta, so.eid, plan->row_of_edge, w, (const T *)relation, (const T *)input, (const T *)output,
-            (const T *)outgrad, (T *)wgrad, (int)plan->E, (int)D);
+            (const T *)outgrad, (T *)wgrad, so.counts, (int)D);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -348,8 +351,10 @@ int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int wha
         case 1: src = so.fix; bytes = (size_t)so.num_fix * 16; break;
         case 2: src = so.nonempty; bytes = (size_t)(so.num_seg + 1) * 4; break;
         case 3: src = so.seg_ptr; bytes = (size_t)(so.num_seg + 1) * 4; break;
-        default: set_error("plan_debug_read: what must be 0 (items), 1 (fix), 2 (nonempty), 3 (seg_ptr)"); return 1;
+        case 4: src = so.counts; bytes = 8 * 4; break;
+        default: set_error("plan_debug_read: what must be 0 (items), 1 (fix), 2 (nonempty), 3 (seg_ptr), 4 (counts)"); return 1;
     }
+    if (plan->masked && (what == 0 || what == 1)) bytes = (size_t)cap_bytes;  // exact sizes live on the device (what = 4)
     if ((int64_t)bytes > cap_bytes) { set_error("plan_debug_read: host buffer too small"); return 1; }
     if (bytes > 0) CUDA_TRY(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
     return 0;
@@ -368,6 +373,11 @@ int ultra_rspmm_plan_build(ultra_rspmm_plan **plan_out, const int64_t *edge_inde
     *plan_out = nullptr;
     return plan_build(plan_out, edge_index, edge_type, num_node, num_edge, num_relation, workspace,
                       workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ultra_rspmm_plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep_mask, void *stream) {
+    if (plan == nullptr) { set_error("null plan"); return 1; }
+    return plan_apply_mask(plan, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
 void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan) {
@@ -416,11 +426,13 @@ int ultra_rspmm_set_edge_weight(ultra_rspmm_plan *plan, const void *edge_weight,
     if (dtype == ULTRA_RSPMM_F32)
         permute_weight_kernel<float><<<blocks, 256, 0, stream>>>(
             (const float *)edge_weight, plan->ord[0].eid, plan->ord[1].eid, plan->ord[2].eid,
-            (float *)plan->ord[0].w, (float *)plan->ord[1].w, (float *)plan->ord[2].w, E, plan->w_nonunit);
+            (float *)plan->ord[0].w, (float *)plan->ord[1].w, (float *)plan->ord[2].w, plan->ord[0].counts,
+            plan->w_nonunit);
     else
         permute_weight_kernel<double><<<blocks, 256, 0, stream>>>(
             (const double *)edge_weight, plan->ord[0].eid, plan->ord[1].eid, plan->ord[2].eid,
-            (double *)plan->ord[0].w, (double *)plan->ord[1].w, (double *)plan->ord[2].w, E, plan->w_nonunit);
+            (double *)plan->ord[0].w, (double *)plan->ord[1].w, (double *)plan->ord[2].w, plan->ord[0].counts,
+            plan->w_nonunit);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

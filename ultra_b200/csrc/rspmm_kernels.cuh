@@ -173,7 +173,9 @@ template <typename T> struct SegParams {
     int *sched;            // {next block ticket, CTAs finished}: dynamic tile-major work queue, reset by the last CTA
     const int *nonempty;
     const int4 *items;
-    int num_warp_items;
+    const int *counts;     // device-side result block of the plan's cutter: [0] num_items, [1] num_fix, [2] num_fix_long,
+                           // [3] num_slots, [7] num_edge.  The launch geometry is derived from it IN the kernel, so a plan
+                           // whose edge set was re-cut on the device (ultra_rspmm_plan_apply_mask) needs no host round trip
     const T *relation;  // (R, D)
     const T *input;     // (N, D)
     const T *output;    // (N, D)   backward only
@@ -189,10 +191,8 @@ template <typename T> struct SegParams {
     int R;
     int N;
     int num_tiles;
-    int units_per_tile;
     int items_per_warp;
     int run;
-    long long total_units;
 };
 
 // which tensors a (MODE, SUM, MUL) combination touches per edge
@@ -535,19 +535,22 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
     // L2-resident - is unchanged.  Results do not depend on which CTA computes a unit.
     // The next ticket is drawn at the START of a block and published at its end, so the atomic's round trip (~1 us,
     // 19 blocks per CTA at C2 = 1 % of the call when it was exposed) overlaps the block's work.
+    const int num_warp_items = __ldg(p.counts) / kSubPerWarp;
+    const int units_per_tile = (num_warp_items + kCtaWarps * p.items_per_warp - 1) / (kCtaWarps * p.items_per_warp);
+    const long long total_units = (long long)units_per_tile * p.num_tiles;
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
     __syncthreads();
     for (;;) {
         const long long blk = s_ticket;
-        if (blk * p.run >= p.total_units) break;
+        if (blk * p.run >= total_units) break;
         int next_ticket = 0;
         if (threadIdx.x == 0) next_ticket = atomicAdd(p.sched, 1);  // consumed only after the block (no stall here)
         for (int uu = 0; uu < p.run; uu++) {
             const long long unit = blk * p.run + uu;
-            if (unit >= p.total_units) break;
-            const int tile = (int)(unit / p.units_per_tile);
-            const int chunk = (int)(unit - (long long)tile * p.units_per_tile);
+            if (unit >= total_units) break;
+            const int tile = (int)(unit / units_per_tile);
+            const int chunk = (int)(unit - (long long)tile * units_per_tile);
             if ((kRelS || kG1S) && tile != cur_tile) {
                 __syncthreads();  // everyone is done reading the previous tile's rows
                 const int grp = tile / p.lay.tpg, tin = tile - grp * p.lay.tpg;
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
 #pragma unroll 1
             for (int k = 0; k < p.items_per_warp; k++) {
                 const int wi = (chunk * p.items_per_warp + k) * kCtaWarps + warp;
-                if (wi < p.num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, meta_s_addr, use_w);
+                if (wi < num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, meta_s_addr, use_w);
             }
         }
         __syncthreads();  // every thread has read this block's ticket
@@ -608,12 +611,14 @@ __device__ __forceinline__ size_t dst_offset(const Layout &lay, long long grp_by
 // fix-up, part 1: long segments fold their chunk-group partials.  One 256-thread CTA per (segment, 128-column
 // chunk): warp w folds partials w, w+8, ... in order, then warp 0 folds the 8 warp results in order -> deterministic.
 template <typename T, int RED>
-__global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restrict__ fix, int num_fix_long,
+__global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restrict__ fix, const int *__restrict__ counts,
                                                             const T *__restrict__ partial, T *__restrict__ dst,
                                                             const T *__restrict__ boundary, int D, Layout lay,
-                                                            long long grp_bytes) {
+                                                            long long grp_bytes, int ncc) {
     constexpr int V = VecN<T>::value;
     __shared__ Vec<T> part[8][32];
+    const int num_fix_long = __ldg(counts + 2);  // the grid is sized for an upper bound (block-uniform exit)
+    if (num_fix_long == 0 || blockIdx.x >= (unsigned)num_fix_long * (unsigned)ncc) return;
     const int f = blockIdx.x % num_fix_long;
     const int cc = blockIdx.x / num_fix_long;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -653,26 +658,30 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(const int4 *__restri
 
 // fix-up, part 2: empty segments get the Nary identity (operator.cuh:53,66,79).  One warp per (segment, 128 columns).
 template <typename T, int RED>
-__global__ void __launch_bounds__(256) fill_identity_kernel(const int4 *__restrict__ fix, int num_fix,
-                                                            T *__restrict__ dst, const T *__restrict__ boundary,
-                                                            int D, Layout lay, long long grp_bytes) {
+__global__ void __launch_bounds__(256) fill_identity_kernel(const int4 *__restrict__ fix_all,
+                                                            const int *__restrict__ counts, T *__restrict__ dst,
+                                                            const T *__restrict__ boundary, int D, Layout lay,
+                                                            long long grp_bytes) {
     constexpr int V = VecN<T>::value;
     const int ncc = (D + 32 * V - 1) / (32 * V);
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int num_long = __ldg(counts + 2), num_fix = __ldg(counts + 1) - num_long;  // empty segments follow the long ones
+    const int4 *fix = fix_all + num_long;
     const int lane = threadIdx.x & 31;
-    if (gw >= (long long)num_fix * ncc) return;
-    const int f = (int)(gw % num_fix);
-    const int cc = (int)(gw / num_fix);
-    const int c0 = cc * 32 * V + lane * V;
-    if (c0 >= D) return;
-    Vec<T> acc;
+    const long long warps = (long long)num_fix * ncc, stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < warps; gw += stride) {
+        const int f = (int)(gw % num_fix);
+        const int cc = (int)(gw / num_fix);
+        const int c0 = cc * 32 * V + lane * V;
+        if (c0 >= D) continue;
+        Vec<T> acc;
 #pragma unroll
-    for (int k = 0; k < V; k++) acc.v[k] = nary_zero<RED, T>();
-    const size_t off = dst_offset<T>(lay, grp_bytes, c0, __ldg(fix + f).x);
-    if (boundary != nullptr) {  // Nary(identity, boundary) == boundary
-        acc = *reinterpret_cast<const Vec<T> *>(reinterpret_cast<const char *>(boundary) + off);
+        for (int k = 0; k < V; k++) acc.v[k] = nary_zero<RED, T>();
+        const size_t off = dst_offset<T>(lay, grp_bytes, c0, __ldg(fix + f).x);
+        if (boundary != nullptr) {  // Nary(identity, boundary) == boundary
+            acc = *reinterpret_cast<const Vec<T> *>(reinterpret_cast<const char *>(boundary) + off);
+        }
+        st_stream(reinterpret_cast<T *>(reinterpret_cast<char *>(dst) + off), acc);
     }
-    st_stream(reinterpret_cast<T *>(reinterpret_cast<char *>(dst) + off), acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -682,11 +691,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const int2 *__restrict__ met
                                                     const int *__restrict__ row_of_edge,
                                                     const T *__restrict__ w, const T *__restrict__ relation,
                                                     const T *__restrict__ input, const T *__restrict__ output,
-                                                    const T *__restrict__ outgrad, T *__restrict__ wgrad, int E,
-                                                    int D) {
+                                                    const T *__restrict__ outgrad, T *__restrict__ wgrad,
+                                                    const int *__restrict__ counts, int D) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (gw >= E) return;
+    if (gw >= __ldg(counts + 7)) return;  // launched for the base graph's edge count
     const int e = (int)gw;
     const int2 m = __ldg(meta + e);
     const int col = m.x, type = m.y & 0x7fffffff, row = __ldg(row_of_edge + e);
@@ -760,10 +769,10 @@ __global__ void __launch_bounds__(256) seg_reduce_generic_kernel(const int2 *__r
 template <typename T>
 __global__ void permute_weight_kernel(const T *__restrict__ w, const int *__restrict__ eid0,
                                       const int *__restrict__ eid1, const int *__restrict__ eid2,
-                                      T *__restrict__ w0, T *__restrict__ w1, T *__restrict__ w2, int E,
-                                      int *__restrict__ nonunit) {
+                                      T *__restrict__ w0, T *__restrict__ w1, T *__restrict__ w2,
+                                      const int *__restrict__ counts, int *__restrict__ nonunit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E) return;
+    if (i >= __ldg(counts + 7)) return;  // launched for the base graph's edge count
     if (w[i] != T(1)) *nonunit = 1;  // benign race: every writer stores the same value
     w0[i] = w[eid0[i]];
     w1[i] = w[eid1[i]];

@@ -6,6 +6,10 @@
 // the edge-balanced work-item lists are cut on the host from the three segment-pointer arrays.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <climits>
 
 #include <algorithm>
 #include <cstring>
@@ -37,6 +41,7 @@ struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
     size_t cut_cnt, cut_incl, rkeys[2], ritems[2], counts;  // device cutter temporaries + per-order result counts
+    size_t meta_m[3], eid_m[3], seg_ptr_m[3], row_of_edge_m, mask_pos;  // masked views (plan_apply_mask)
     int64_t max_blocks, rest_cap;
 };
 
@@ -72,6 +77,13 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
         L.ritems[k] = take((size_t)L.rest_cap * 16);
     }
     L.counts = take(3 * kPlanCounts * sizeof(int));
+    for (int o = 0; o < 3; o++) {
+        L.meta_m[o] = take((size_t)E * 8);
+        L.eid_m[o] = take((size_t)E * 4);
+        L.seg_ptr_m[o] = take((size_t)(S[o] + 1) * 4);
+    }
+    L.row_of_edge_m = take((size_t)E * 4);
+    L.mask_pos = take((size_t)E * 4);
     L.total = off;
     return L;
 }
@@ -261,7 +273,7 @@ __global__ void cut_write_kernel(const int *__restrict__ ptr, int S, const CutCo
 
 // sorted rest items -> behind the merged groups; pad to a multiple of 4; result counts for the launchers
 __global__ void cut_finalize_kernel(const CutCounts *__restrict__ incl, int nb, const int4 *__restrict__ sorted, int4 *items,
-                                    int *nonempty, int *counts) {
+                                    int *nonempty, int *counts, int num_edge, const int *num_edge_dev) {
     const CutCounts tot = incl[nb - 1];
     const int G4 = tot.groups * kSubPerWarp, rest = tot.whole + tot.chunks;
     const int padded = (rest + kSubPerWarp - 1) / kSubPerWarp * kSubPerWarp;
@@ -276,13 +288,13 @@ __global__ void cut_finalize_kernel(const CutCounts *__restrict__ incl, int nb, 
         counts[4] = tot.nonempty + 1;        // entries of nonempty (incl. the pad)
         counts[5] = tot.groups;
         counts[6] = rest;
-        counts[7] = 0;
+        counts[7] = num_edge_dev ? *num_edge_dev : num_edge;  // edges of the (possibly masked) graph
     }
 }
 
 // Device cutter for one segment order: count -> scan -> write -> sort the non-group items -> finalize.  No host sync.
 int cut_items_device(const int *seg_ptr, int S, int64_t E, const WsLayout &L, char *ws, SegOrder &so, int *counts,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const int *num_edge_dev = nullptr) {
     const int nb = std::max(1, (S + kCutBlock - 1) / kCutBlock);
     auto *cnt = reinterpret_cast<CutCounts *>(ws + L.cut_cnt);
     auto *incl = reinterpret_cast<CutCounts *>(ws + L.cut_incl);
@@ -308,7 +320,7 @@ int cut_items_device(const int *seg_ptr, int S, int64_t E, const WsLayout &L, ch
     temp_bytes = L.cub_temp_bytes;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, temp_bytes, dk, dv, cap, 0, 39, stream));  // 7 + 32 key bits
     cut_finalize_kernel<<<std::max(1, std::min(cap / 256, 64)), 256, 0, stream>>>(incl, nb, dv.Current(), so.items,
-                                                                                  so.nonempty, counts);
+                                                                                  so.nonempty, counts, (int)E, num_edge_dev);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -402,8 +414,17 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         so.fix = reinterpret_cast<int4 *>(ws + L.fix[o]);
         so.w = ws + L.w[o];
         so.num_seg = (int)S[o];
+        so.meta_base = so.meta; so.eid_base = so.eid; so.seg_ptr_base = so.seg_ptr;
+        so.meta_mask = reinterpret_cast<int2 *>(ws + L.meta_m[o]);
+        so.eid_mask = reinterpret_cast<int *>(ws + L.eid_m[o]);
+        so.seg_ptr_mask = reinterpret_cast<int *>(ws + L.seg_ptr_m[o]);
+        so.counts = reinterpret_cast<const int *>(ws + L.counts) + o * kPlanCounts;
     }
+    plan->ws = ws;
     plan->row_of_edge = reinterpret_cast<int *>(ws + L.row_of_edge);
+    plan->row_of_edge_base = plan->row_of_edge;
+    plan->row_of_edge_mask = reinterpret_cast<int *>(ws + L.row_of_edge_m);
+    plan->mask_pos = reinterpret_cast<int *>(ws + L.mask_pos);
     auto *keysA = reinterpret_cast<unsigned long long *>(ws + L.keysA);
     auto *keysB = reinterpret_cast<unsigned long long *>(ws + L.keysB);
     auto *valsA = reinterpret_cast<int *>(ws + L.valsA);
@@ -463,9 +484,112 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         SegOrder &so = plan->ord[o];
         const int *c = h + 4 + o * kPlanCounts;
         so.num_items = c[0]; so.num_fix = c[1]; so.num_fix_long = c[2]; so.num_slots = c[3];
+        so.base_items = c[0]; so.base_fix = c[1]; so.base_fix_long = c[2]; so.base_slots = c[3];
         if ((int64_t)so.num_items > max_items(E, S[o])) { set_error("plan_build: item bound exceeded"); return 4; }
     }
     *out = plan.release();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Edge masks: the sub-graph that keeps a subset of the base graph's edges, re-cut WITHOUT sorting and WITHOUT a host
+// synchronisation (the reference re-sorts the masked edge list inside every rspmm call of a training step,
+// /root/reference/ultra/base_nbfnet.py:54-77 + /root/reference/ultra/rspmm/rspmm.py:174-178).  Removing edges keeps every
+// order sorted, so per order: scan the keep flags in plan order -> compact metadata / edge ids -> gather the new segment
+// pointer from the scan -> re-flag the last edge of every segment -> run the device cutter on the new pointer.  The host
+// never learns the new counts: it keeps upper bounds for grid and scratch sizing, the kernels read the exact ones.
+namespace {
+
+struct KeepInOrder {  // keep flag of the i-th edge of a plan order
+    const unsigned char *keep;
+    const int *eid;
+    __host__ __device__ int operator()(int i) const { return keep[eid[i]] ? 1 : 0; }
+};
+
+__global__ void mask_compact_kernel(const unsigned char *__restrict__ keep, const int *__restrict__ pos,
+                                    const int2 *__restrict__ meta_b,
+                                    const int *__restrict__ eid_b, const int *__restrict__ row_b, int2 *__restrict__ meta_m,
+                                    int *__restrict__ eid_m, int *__restrict__ row_m, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    const int e = eid_b[i];
+    if (!keep[e]) return;
+    const int j = pos[i] - 1;  // inclusive scan
+    const int2 m = meta_b[i];
+    meta_m[j] = make_int2(m.x, m.y & 0x7fffffff);  // last-of-segment flags are set again below
+    eid_m[j] = e;  // still the caller's BASE edge id: edge weights / weight_grad keep the base graph's length and order
+    if (row_m != nullptr) row_m[j] = row_b[i];
+}
+
+__global__ void mask_segptr_kernel(const int *__restrict__ seg_ptr_b, const int *__restrict__ pos, int *__restrict__ seg_ptr_m,
+                                   int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > S) return;
+    const int b = seg_ptr_b[s];
+    seg_ptr_m[s] = b > 0 ? pos[b - 1] : 0;
+}
+
+__global__ void mask_lastflag_kernel(const int *__restrict__ seg_ptr_m, int2 *__restrict__ meta_m, int S, int *num_edge_out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0 && num_edge_out != nullptr) *num_edge_out = seg_ptr_m[S];
+    if (s >= S) return;
+    const int e = seg_ptr_m[s + 1];
+    if (e > seg_ptr_m[s]) meta_m[e - 1].y |= 0x80000000;
+}
+
+}  // namespace
+
+int plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep, cudaStream_t stream) {
+    const int64_t N = plan->N, E = plan->E, R = plan->R;
+    const WsLayout L = make_layout(N, E, R);
+    char *ws = static_cast<char *>(plan->ws);
+    int *counts = reinterpret_cast<int *>(ws + L.counts);
+    const int64_t S[3] = {N, N, R};
+    if (keep == nullptr) {  // back to the base graph: base arrays, exact counts, items re-cut from the base pointer
+        if (!plan->masked) return 0;
+        for (int o = 0; o < 3; o++) {
+            SegOrder &so = plan->ord[o];
+            so.meta = so.meta_base; so.eid = so.eid_base; so.seg_ptr = so.seg_ptr_base;
+            so.num_items = so.base_items; so.num_fix = so.base_fix; so.num_fix_long = so.base_fix_long;
+            so.num_slots = so.base_slots;
+            if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream)) return rc;
+        }
+        plan->row_of_edge = plan->row_of_edge_base;
+        plan->masked = false;
+        return 0;
+    }
+    if (E == 0) return 0;
+    const int threads = 256, blocks = (int)((E + threads - 1) / threads);
+    size_t temp_bytes = 0;
+    for (int o = 0; o < 3; o++) {
+        SegOrder &so = plan->ord[o];
+        cub::TransformInputIterator<int, KeepInOrder, cub::CountingInputIterator<int>> in_o(
+            cub::CountingInputIterator<int>(0), KeepInOrder{keep, so.eid_base});
+        temp_bytes = L.cub_temp_bytes;
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub_temp, temp_bytes, in_o, plan->mask_pos, (int)E, stream));
+        mask_compact_kernel<<<blocks, threads, 0, stream>>>(keep, plan->mask_pos, so.meta_base, so.eid_base,
+                                                            o == 0 ? plan->row_of_edge_base : nullptr, so.meta_mask,
+                                                            so.eid_mask, o == 0 ? plan->row_of_edge_mask : nullptr, (int)E);
+        CUDA_TRY(cudaGetLastError());
+        const int sblocks = (int)((S[o] + 1 + threads - 1) / threads);
+        mask_segptr_kernel<<<sblocks, threads, 0, stream>>>(so.seg_ptr_base, plan->mask_pos, so.seg_ptr_mask, (int)S[o]);
+        CUDA_TRY(cudaGetLastError());
+        int *num_edge_dev = counts + o * kPlanCounts + 7;  // finalize reads it back from here (same slot)
+        mask_lastflag_kernel<<<sblocks, threads, 0, stream>>>(so.seg_ptr_mask, so.meta_mask, (int)S[o], num_edge_dev);
+        CUDA_TRY(cudaGetLastError());
+        so.meta = so.meta_mask; so.eid = so.eid_mask; so.seg_ptr = so.seg_ptr_mask;
+        if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream, num_edge_dev))
+            return rc;
+        // host-side upper bounds for grids and scratch (a merged group that loses edges can break into 4 single chunks,
+        // so slots are bounded by the chunk count, not by the base graph's slot count)
+        so.num_items = so.base_items;                   // a HINT for grid / run sizing only: the kernel derives its units from
+                                                        // the device-side count and the persistent CTAs draw tickets until done
+        so.num_fix_long = so.base_fix_long;             // a sub-graph's long segments are a subset of the base graph's
+        so.num_fix = so.base_fix_long + (int)S[o];      // ... but any segment may have become empty
+        so.num_slots = (int)((E + kItemEdges - 1) / kItemEdges) + so.base_fix_long;
+    }
+    plan->row_of_edge = plan->row_of_edge_mask;
+    plan->masked = true;
     return 0;
 }
 

@@ -18,10 +18,19 @@ struct SegOrder {
     int4 *fix = nullptr;       // (num_fix)
     void *w = nullptr;         // (E) weights in this order, dtype of the last set_edge_weight
     int num_seg = 0;
+    // Host copies of the cutter's counts.  For the base graph they are exact; while an edge mask is applied
+    // (ultra_rspmm_plan_apply_mask) they are UPPER BOUNDS used only to size grids and scratch - the kernels read the
+    // exact values from the device-side block `counts`.
     int num_items = 0;
     int num_fix = 0;
     int num_fix_long = 0;      // fix[0 .. num_fix_long) are long segments, the rest are empty segments
     int num_slots = 0;
+    const int *counts = nullptr;  // device: {num_items, num_fix, num_fix_long, num_slots, nonempty entries, groups, rest, num_edge}
+    // base-graph arrays / exact counts (the active pointers above switch between these and the masked copies)
+    int2 *meta_base = nullptr, *meta_mask = nullptr;
+    int *eid_base = nullptr, *eid_mask = nullptr;
+    int *seg_ptr_base = nullptr, *seg_ptr_mask = nullptr;
+    int base_items = 0, base_fix = 0, base_fix_long = 0, base_slots = 0;
 };
 
 struct HostLanes;  // rspmm_api.cu: streams / events of the host-buffer pipeline, created on first use
@@ -32,6 +41,10 @@ struct ultra_rspmm_plan {
     int64_t N = 0, E = 0, R = 0;
     ultra::SegOrder ord[3];  // FWD (by row), BWD_IN (by col), BWD_REL (by relation)
     int *row_of_edge = nullptr;  // (E) row of each edge in FWD order (weight_grad kernel)
+    int *row_of_edge_base = nullptr, *row_of_edge_mask = nullptr;
+    int *mask_pos = nullptr;     // (E) scratch of apply_mask: compaction positions
+    bool masked = false;
+    void *ws = nullptr;          // the caller's workspace (cutter temporaries live there)
     int *w_nonunit = nullptr;    // device flag: some bound weight != 1
     int *counts = nullptr;       // (3 orders x 8) device copy of {num_items, num_fix, num_fix_long, num_slots, ...}
     int *sched = nullptr;        // (3 orders x 2) device work-queue tickets {next block, CTAs done}; self-resetting
@@ -52,6 +65,9 @@ size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
                    int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
                    int64_t nonempty_cap, int *num_nonempty);
+// Re-cut the plan for the sub-graph that keeps edge e iff keep[e] != 0 (device bytes in the CALLER's edge order), entirely
+// on the device and without a host synchronisation; keep == nullptr restores the base graph.
+int plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep, cudaStream_t stream);
 int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t *edge_type, int64_t N, int64_t E,
                int64_t R, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace ultra

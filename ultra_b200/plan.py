@@ -63,6 +63,7 @@ class GraphPlan:
         self._scratch = None
         self._weight_key = None
         self.sm_limit = 0
+        self.masked = False
 
     def nbytes(self):
         """Device bytes this plan pins (workspace + scratch + host-path staging), for the cache's byte budget."""
@@ -115,6 +116,23 @@ class GraphPlan:
         _capi.check(rc, "ultra_rspmm_set_edge_weight")
         self._weight_key = key
         self._weight_ref = edge_weight  # keep the storage alive so the key cannot be recycled
+
+    def apply_edge_mask(self, keep_mask):
+        """Re-cut this plan for the sub-graph that keeps edge e iff keep_mask[e] (bool (E,), caller's edge order) - on the
+        device, no sort, no host synchronisation, CUDA-graph capturable (ultra_rspmm_plan_apply_mask).  The incremental
+        plan for remove_easy_edges (/root/reference/ultra/base_nbfnet.py:54-77): afterwards every rspmm call on this graph's
+        (unchanged) edge tensors computes on the masked edge set, exactly like a plan built from `edge_index[:, mask]`.
+        `None` restores the base graph.  The mask is plan state: forward and the matching backward must see the same one."""
+        if keep_mask is not None and (keep_mask.dtype != torch.bool or keep_mask.shape != (self.num_edge,)
+                                      or keep_mask.device != self.device):
+            raise RuntimeError("apply_edge_mask: keep_mask must be a bool vector of length num_edge on the plan's device")
+        km = None if keep_mask is None else keep_mask.contiguous()
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().ultra_rspmm_plan_apply_mask(self._handle, None if km is None else km.data_ptr(),
+                                                         _stream_ptr(self.device))
+        _capi.check(rc, "ultra_rspmm_plan_apply_mask")
+        self._mask_ref = km  # the kernels enqueued above read it asynchronously
+        self.masked = km is not None
 
     def edge_mask_weight(self, keep_mask, dtype=torch.float32):
         """A 0/1 edge-weight vector that REMOVES the edges where `keep_mask` is False - the incremental alternative to a
