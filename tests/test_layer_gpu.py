@@ -508,3 +508,32 @@ def test_training_step_with_edge_mask_is_cuda_graph_capturable(cuda_device):
         layer.relation = s_rel
         for p, g in zip([s_x, s_rel] + params, zero_ref):
             p.grad = g
+
+
+def test_ultra_nbfnet_edge_mask_equals_filtered_graph(cuda_device):
+    """UltraNBFNet.forward(edge_mask=...) - the runner's remove_easy_edges: the entity graph's plan re-cut on the device
+    (ultra_rspmm_plan_apply_mask) - gives the scores of the same model on the physically filtered edge list, bit for bit;
+    without the mask the base graph is back."""
+    from ultra_b200.nbfnet import UltraNBFNet
+    from ultra_b200.synth import synth_kg, relation_graph_of
+    dev = cuda_device
+    torch.manual_seed(31)
+    ei, et, R = synth_kg(500, 6, 4000, alpha=1.0, seed=7)
+    N = 500
+    ei, et = ei.to(dev), et.to(dev)
+    rei, ret, rR, rN = relation_graph_of(ei, et, N, R)
+    model = UltraNBFNet().to(dev).eval()
+    g = torch.Generator().manual_seed(8)
+    pick = torch.randint(0, ei.shape[1] // 2, (6,), generator=g).to(dev)  # direct (non-inverse) triples
+    h, t, r = ei[0, pick], ei[1, pick], et[pick]
+    keep = UltraNBFNet.easy_edge_mask(ei, et, N, R, h, t, r)
+    assert int((~keep).sum()) >= 6
+    rel_graph, graph = (rei.contiguous(), ret.contiguous(), rN), (ei, et, N)
+    with torch.no_grad():
+        base = model(rel_graph, graph, h, r)
+        masked = model(rel_graph, graph, h, r, edge_mask=keep)
+        filtered = model(rel_graph, (ei[:, keep].contiguous(), et[keep].contiguous(), N), h, r)
+        again = model(rel_graph, graph, h, r)
+    assert torch.equal(masked, filtered)
+    assert torch.equal(again, base)
+    assert not torch.equal(masked, base)

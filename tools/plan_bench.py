@@ -28,5 +28,22 @@ for name in ("wn18rr", "fb15k237", "codex_l"):
         assert (k2.diff() >= 0).all()
     torch.cuda.synchronize()
     ref_ms = 1e3 * (time.perf_counter() - t0) / 5
+    # incremental re-cut for a masked edge set (training's remove_easy_edges): device time (CUDA events: nothing syncs)
+    # and host wall time of the enqueue
+    p = GraphPlan(ei, et, N, R)
+    keep = torch.rand(ei.shape[1], device=d) > 0.002
+    for _ in range(3):
+        p.apply_edge_mask(keep)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(10):
+        p.apply_edge_mask(keep)
+    b.record()
+    enqueue_ms = 1e3 * (time.perf_counter() - t0) / 10
+    torch.cuda.synchronize()
+    mask_ms = a.elapsed_time(b) / 10
     print(json.dumps({"graph": name, "E": ei.shape[1], "plan_build_ms_min": round(min(ts), 3), "plan_build_ms_med": round(sorted(ts)[2], 3),
+                      "apply_mask_device_ms": round(mask_ms, 3), "apply_mask_enqueue_ms": round(enqueue_ms, 3),
                       "reference_per_call_sort_ms": round(ref_ms, 3)}))

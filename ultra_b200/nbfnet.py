@@ -105,8 +105,8 @@ class UltraNBFNet(nn.Module):
         """keep-mask of remove_easy_edges (/root/reference/ultra/base_nbfnet.py:54-77): False for every edge
         (h, t, r) / (t, h, r + R/2) of the training batch (or every edge between the pairs when remove_one_hop).  The
         reference's edge_match (tasks.py:7-39) is a hashing + bucketize search; an integer-key `isin` gives the same set.
-        Returns a bool (E,) tensor: feed it to the forward as `edge_mask` - for the sum aggregate it is applied as a 0/1
-        edge weight on the base graph's plan, nothing is re-sorted (see GraphPlan.edge_mask_weight)."""
+        Returns a bool (E,) tensor: feed it to the forward as `edge_mask` - the base graph's plan is re-cut for it on the
+        device (GraphPlan.apply_edge_mask), nothing is re-sorted and the host is never synchronised."""
         h = torch.cat([h_index.flatten(), t_index.flatten()])
         t = torch.cat([t_index.flatten(), h_index.flatten()])
         key = edge_index[0] * num_node + edge_index[1]
@@ -162,9 +162,16 @@ class UltraNBFNet(nn.Module):
             relations = [p(rel_repr) for p in projections]
         boundary = self._boundary(h_index, query, num_node)
         weight = None
-        if edge_mask is not None:
+        if edge_index.is_cuda:
+            # the incremental plan (ultra_rspmm_plan_apply_mask): re-cut on the device for this step's edge set, no sort,
+            # no host sync; all six layers and their backward passes then run on the masked plan.  None restores the graph.
+            from .plan import plan_cache
+            plan = plan_cache.get(edge_index, edge_type, num_node, rel_repr.shape[1])
+            if edge_mask is not None or plan.masked:
+                plan.apply_edge_mask(edge_mask)
+        elif edge_mask is not None:  # CPU tensors (tests with the oracle): a 0/1 weight is an edge removal for `sum`
             if layers[0].aggregate_func != "sum":
-                raise ValueError("edge_mask is applied as a 0/1 edge weight, which is only an edge removal for `sum`")
+                raise ValueError("edge_mask as a 0/1 edge weight is only an edge removal for `sum`")
             weight = edge_mask.to(boundary.dtype)
         return self._bellmanford(layers, boundary, query, edge_index, edge_type, num_node, relations, hook, weight), query
 
