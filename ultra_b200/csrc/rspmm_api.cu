@@ -309,6 +309,15 @@ struct ultra::HostLanes {
 
 using namespace ultra;
 
+ultra_rspmm_plan::~ultra_rspmm_plan() {
+    delete host_lanes;
+    for (int i = 0; i < 2; i++) {
+        if (side[i]) cudaStreamDestroy(side[i]);
+        if (side_ev[i]) cudaEventDestroy(side_ev[i]);
+    }
+    if (fork_ev) cudaEventDestroy(fork_ev);
+}
+
 extern "C" {
 
 const char *ultra_rspmm_version(void) { return "ultra_rspmm sm_100a 0.1.0"; }
@@ -381,7 +390,6 @@ int ultra_rspmm_plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *kee
 }
 
 void ultra_rspmm_plan_destroy(ultra_rspmm_plan *plan) {
-    if (plan != nullptr) delete plan->host_lanes;
     delete plan;
 }
 

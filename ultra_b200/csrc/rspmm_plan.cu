@@ -40,8 +40,9 @@ inline int64_t max_items(int64_t E, int64_t S) { return 5 * ((E + kItemEdges - 1
 struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
-    size_t cut_cnt, cut_incl, rkeys[2], ritems[2], counts;  // device cutter temporaries + per-order result counts
-    size_t meta_m[3], eid_m[3], seg_ptr_m[3], row_of_edge_m, mask_pos;  // masked views (plan_apply_mask)
+    // device cutter / mask temporaries, one set PER ORDER (the three orders are processed on three streams), + result counts
+    size_t cut_cnt[3], cut_incl[3], rkeys[3][2], ritems[3][2], cut_temp[3], cut_temp_bytes, counts;
+    size_t meta_m[3], eid_m[3], seg_ptr_m[3], row_of_edge_m, mask_pos[3];  // masked views (plan_apply_mask)
     int64_t max_blocks, rest_cap;
 };
 
@@ -70,11 +71,16 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
     const int64_t Smax = std::max(N, R);
     L.max_blocks = (Smax + kCutBlock - 1) / kCutBlock + 1;
     L.rest_cap = max_items(E, Smax);
-    L.cut_cnt = take((size_t)L.max_blocks * sizeof(CutCounts));
-    L.cut_incl = take((size_t)L.max_blocks * sizeof(CutCounts));
-    for (int k = 0; k < 2; k++) {
-        L.rkeys[k] = take((size_t)L.rest_cap * 8);
-        L.ritems[k] = take((size_t)L.rest_cap * 16);
+    L.cut_temp_bytes = (size_t)(2 << 20) + (size_t)E / 32;
+    for (int o = 0; o < 3; o++) {
+        L.cut_cnt[o] = take((size_t)L.max_blocks * sizeof(CutCounts));
+        L.cut_incl[o] = take((size_t)L.max_blocks * sizeof(CutCounts));
+        for (int k = 0; k < 2; k++) {
+            L.rkeys[o][k] = take((size_t)L.rest_cap * 8);
+            L.ritems[o][k] = take((size_t)L.rest_cap * 16);
+        }
+        L.cut_temp[o] = take(L.cut_temp_bytes);
+        L.mask_pos[o] = take((size_t)E * 4);
     }
     L.counts = take(3 * kPlanCounts * sizeof(int));
     for (int o = 0; o < 3; o++) {
@@ -83,7 +89,6 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
         L.seg_ptr_m[o] = take((size_t)(S[o] + 1) * 4);
     }
     L.row_of_edge_m = take((size_t)E * 4);
-    L.mask_pos = take((size_t)E * 4);
     L.total = off;
     return L;
 }
@@ -292,33 +297,64 @@ __global__ void cut_finalize_kernel(const CutCounts *__restrict__ incl, int nb, 
     }
 }
 
+// Fork the caller's stream into three lanes (lane 0 IS the caller's stream, lanes 1-2 are plan-owned side streams created
+// on first use) and join them back; works under CUDA-graph capture (the lanes become parallel branches of the graph).
+struct ForkJoin {
+    ultra_rspmm_plan *plan;
+    cudaStream_t main;
+    int rc = 0;
+    ForkJoin(ultra_rspmm_plan *p, cudaStream_t s) : plan(p), main(s) {
+        for (int i = 0; i < 2 && rc == 0; i++) {
+            if (plan->side[i] == nullptr && cudaStreamCreateWithFlags(&plan->side[i], cudaStreamNonBlocking) != cudaSuccess) rc = 2;
+            if (rc == 0 && plan->side_ev[i] == nullptr &&
+                cudaEventCreateWithFlags(&plan->side_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = 2;
+        }
+        if (rc == 0 && plan->fork_ev == nullptr && cudaEventCreateWithFlags(&plan->fork_ev, cudaEventDisableTiming) != cudaSuccess) rc = 2;
+        if (rc == 0 && cudaEventRecord(plan->fork_ev, main) != cudaSuccess) rc = 2;
+        for (int i = 0; i < 2 && rc == 0; i++)
+            if (cudaStreamWaitEvent(plan->side[i], plan->fork_ev, 0) != cudaSuccess) rc = 2;
+        if (rc) set_error("plan: could not fork the side streams");
+    }
+    cudaStream_t lane(int o) const { return o == 0 ? main : plan->side[o - 1]; }
+    int join() {
+        for (int i = 0; i < 2; i++) {
+            if (cudaEventRecord(plan->side_ev[i], plan->side[i]) != cudaSuccess ||
+                cudaStreamWaitEvent(main, plan->side_ev[i], 0) != cudaSuccess) {
+                set_error("plan: could not join the side streams");
+                return 2;
+            }
+        }
+        return 0;
+    }
+};
+
 // Device cutter for one segment order: count -> scan -> write -> sort the non-group items -> finalize.  No host sync.
-int cut_items_device(const int *seg_ptr, int S, int64_t E, const WsLayout &L, char *ws, SegOrder &so, int *counts,
+int cut_items_device(int o, const int *seg_ptr, int S, int64_t E, const WsLayout &L, char *ws, SegOrder &so, int *counts,
                      cudaStream_t stream, const int *num_edge_dev = nullptr) {
     const int nb = std::max(1, (S + kCutBlock - 1) / kCutBlock);
-    auto *cnt = reinterpret_cast<CutCounts *>(ws + L.cut_cnt);
-    auto *incl = reinterpret_cast<CutCounts *>(ws + L.cut_incl);
+    auto *cnt = reinterpret_cast<CutCounts *>(ws + L.cut_cnt[o]);
+    auto *incl = reinterpret_cast<CutCounts *>(ws + L.cut_incl[o]);
     const int cap = (int)std::min<int64_t>(max_items(E, S), L.rest_cap);
-    cub::DoubleBuffer<unsigned long long> dk(reinterpret_cast<unsigned long long *>(ws + L.rkeys[0]),
-                                             reinterpret_cast<unsigned long long *>(ws + L.rkeys[1]));
-    cub::DoubleBuffer<int4> dv(reinterpret_cast<int4 *>(ws + L.ritems[0]), reinterpret_cast<int4 *>(ws + L.ritems[1]));
+    cub::DoubleBuffer<unsigned long long> dk(reinterpret_cast<unsigned long long *>(ws + L.rkeys[o][0]),
+                                             reinterpret_cast<unsigned long long *>(ws + L.rkeys[o][1]));
+    cub::DoubleBuffer<int4> dv(reinterpret_cast<int4 *>(ws + L.ritems[o][0]), reinterpret_cast<int4 *>(ws + L.ritems[o][1]));
     const int threads = 128, blocks = (nb + threads - 1) / threads;
     cut_count_kernel<<<blocks, threads, 0, stream>>>(seg_ptr, S, cnt, nb);
     CUDA_TRY(cudaGetLastError());
     size_t temp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, temp_bytes, cnt, incl, CutSum(), nb, stream));
-    if (temp_bytes > L.cub_temp_bytes) { set_error("plan_build: internal scan scratch under-reserved"); return 4; }
-    temp_bytes = L.cub_temp_bytes;
-    CUDA_TRY(cub::DeviceScan::InclusiveScan(ws + L.cub_temp, temp_bytes, cnt, incl, CutSum(), nb, stream));
+    if (temp_bytes > L.cut_temp_bytes) { set_error("plan_build: internal scan scratch under-reserved"); return 4; }
+    temp_bytes = L.cut_temp_bytes;
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(ws + L.cut_temp[o], temp_bytes, cnt, incl, CutSum(), nb, stream));
     CUDA_TRY(cudaMemsetAsync(dk.Current(), 0xff, (size_t)cap * 8, stream));  // unused entries sort to the end
     cut_write_kernel<<<blocks, threads, 0, stream>>>(seg_ptr, S, incl, nb, so.items, dk.Current(), dv.Current(), so.fix,
                                                      so.nonempty);
     CUDA_TRY(cudaGetLastError());
     temp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, cap, 0, 39, stream));
-    if (temp_bytes > L.cub_temp_bytes) { set_error("plan_build: internal sort scratch under-reserved"); return 4; }
-    temp_bytes = L.cub_temp_bytes;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, temp_bytes, dk, dv, cap, 0, 39, stream));  // 7 + 32 key bits
+    if (temp_bytes > L.cut_temp_bytes) { set_error("plan_build: internal sort scratch under-reserved"); return 4; }
+    temp_bytes = L.cut_temp_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cut_temp[o], temp_bytes, dk, dv, cap, 0, 39, stream));  // 7 + 32 key bits
     cut_finalize_kernel<<<std::max(1, std::min(cap / 256, 64)), 256, 0, stream>>>(incl, nb, dv.Current(), so.items,
                                                                                   so.nonempty, counts, (int)E, num_edge_dev);
     CUDA_TRY(cudaGetLastError());
@@ -424,7 +460,6 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
     plan->row_of_edge = reinterpret_cast<int *>(ws + L.row_of_edge);
     plan->row_of_edge_base = plan->row_of_edge;
     plan->row_of_edge_mask = reinterpret_cast<int *>(ws + L.row_of_edge_m);
-    plan->mask_pos = reinterpret_cast<int *>(ws + L.mask_pos);
     auto *keysA = reinterpret_cast<unsigned long long *>(ws + L.keysA);
     auto *keysB = reinterpret_cast<unsigned long long *>(ws + L.keysB);
     auto *valsA = reinterpret_cast<int *>(ws + L.valsA);
@@ -468,7 +503,15 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
         } else {
             CUDA_TRY(cudaMemsetAsync(so.seg_ptr, 0, (size_t)(S[o] + 1) * 4, stream));
         }
-        if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream)) return rc;
+    }
+    {   // the three cutters are chains of tiny kernels: run them side by side
+        ForkJoin fj(plan.get(), stream);
+        if (fj.rc) return fj.rc;
+        for (int o = 0; o < 3; o++)
+            if (int rc = cut_items_device(o, plan->ord[o].seg_ptr, (int)S[o], E, L, ws, plan->ord[o], counts + o * kPlanCounts,
+                                          fj.lane(o)))
+                return rc;
+        if (int rc = fj.join()) return rc;
     }
     // the one synchronisation of a plan build: validation flags + the three orders' item / fix / slot counts
     int h[4 + 3 * kPlanCounts];
@@ -545,40 +588,44 @@ int plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep, cudaStrea
     char *ws = static_cast<char *>(plan->ws);
     int *counts = reinterpret_cast<int *>(ws + L.counts);
     const int64_t S[3] = {N, N, R};
+    ForkJoin fj(plan, stream);  // the three orders are independent chains of small kernels: three streams
+    if (fj.rc) return fj.rc;
     if (keep == nullptr) {  // back to the base graph: base arrays, exact counts, items re-cut from the base pointer
-        if (!plan->masked) return 0;
+        if (!plan->masked) return fj.join();
         for (int o = 0; o < 3; o++) {
             SegOrder &so = plan->ord[o];
             so.meta = so.meta_base; so.eid = so.eid_base; so.seg_ptr = so.seg_ptr_base;
             so.num_items = so.base_items; so.num_fix = so.base_fix; so.num_fix_long = so.base_fix_long;
             so.num_slots = so.base_slots;
-            if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream)) return rc;
+            if (int rc = cut_items_device(o, so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, fj.lane(o)))
+                return rc;
         }
         plan->row_of_edge = plan->row_of_edge_base;
         plan->masked = false;
-        return 0;
+        return fj.join();
     }
-    if (E == 0) return 0;
+    if (E == 0) return fj.join();
     const int threads = 256, blocks = (int)((E + threads - 1) / threads);
-    size_t temp_bytes = 0;
     for (int o = 0; o < 3; o++) {
         SegOrder &so = plan->ord[o];
+        cudaStream_t st = fj.lane(o);
+        int *pos = reinterpret_cast<int *>(ws + L.mask_pos[o]);
         cub::TransformInputIterator<int, KeepInOrder, cub::CountingInputIterator<int>> in_o(
             cub::CountingInputIterator<int>(0), KeepInOrder{keep, so.eid_base});
-        temp_bytes = L.cub_temp_bytes;
-        CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub_temp, temp_bytes, in_o, plan->mask_pos, (int)E, stream));
-        mask_compact_kernel<<<blocks, threads, 0, stream>>>(keep, plan->mask_pos, so.meta_base, so.eid_base,
-                                                            o == 0 ? plan->row_of_edge_base : nullptr, so.meta_mask,
-                                                            so.eid_mask, o == 0 ? plan->row_of_edge_mask : nullptr, (int)E);
+        size_t temp_bytes = L.cut_temp_bytes;
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cut_temp[o], temp_bytes, in_o, pos, (int)E, st));
+        mask_compact_kernel<<<blocks, threads, 0, st>>>(keep, pos, so.meta_base, so.eid_base,
+                                                        o == 0 ? plan->row_of_edge_base : nullptr, so.meta_mask,
+                                                        so.eid_mask, o == 0 ? plan->row_of_edge_mask : nullptr, (int)E);
         CUDA_TRY(cudaGetLastError());
         const int sblocks = (int)((S[o] + 1 + threads - 1) / threads);
-        mask_segptr_kernel<<<sblocks, threads, 0, stream>>>(so.seg_ptr_base, plan->mask_pos, so.seg_ptr_mask, (int)S[o]);
+        mask_segptr_kernel<<<sblocks, threads, 0, st>>>(so.seg_ptr_base, pos, so.seg_ptr_mask, (int)S[o]);
         CUDA_TRY(cudaGetLastError());
         int *num_edge_dev = counts + o * kPlanCounts + 7;  // finalize reads it back from here (same slot)
-        mask_lastflag_kernel<<<sblocks, threads, 0, stream>>>(so.seg_ptr_mask, so.meta_mask, (int)S[o], num_edge_dev);
+        mask_lastflag_kernel<<<sblocks, threads, 0, st>>>(so.seg_ptr_mask, so.meta_mask, (int)S[o], num_edge_dev);
         CUDA_TRY(cudaGetLastError());
         so.meta = so.meta_mask; so.eid = so.eid_mask; so.seg_ptr = so.seg_ptr_mask;
-        if (int rc = cut_items_device(so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, stream, num_edge_dev))
+        if (int rc = cut_items_device(o, so.seg_ptr, (int)S[o], E, L, ws, so, counts + o * kPlanCounts, st, num_edge_dev))
             return rc;
         // host-side upper bounds for grids and scratch (a merged group that loses edges can break into 4 single chunks,
         // so slots are bounded by the chunk count, not by the base graph's slot count)
@@ -588,6 +635,7 @@ int plan_apply_mask(ultra_rspmm_plan *plan, const unsigned char *keep, cudaStrea
         so.num_fix = so.base_fix_long + (int)S[o];      // ... but any segment may have become empty
         so.num_slots = (int)((E + kItemEdges - 1) / kItemEdges) + so.base_fix_long;
     }
+    if (int rc = fj.join()) return rc;
     plan->row_of_edge = plan->row_of_edge_mask;
     plan->masked = true;
     return 0;

@@ -38,11 +38,13 @@ struct HostLanes;  // rspmm_api.cu: streams / events of the host-buffer pipeline
 }  // namespace ultra
 
 struct ultra_rspmm_plan {
+    ~ultra_rspmm_plan();  // rspmm_api.cu: releases the plan-owned streams / events (never device memory: the caller owns it)
     int64_t N = 0, E = 0, R = 0;
     ultra::SegOrder ord[3];  // FWD (by row), BWD_IN (by col), BWD_REL (by relation)
     int *row_of_edge = nullptr;  // (E) row of each edge in FWD order (weight_grad kernel)
     int *row_of_edge_base = nullptr, *row_of_edge_mask = nullptr;
-    int *mask_pos = nullptr;     // (E) scratch of apply_mask: compaction positions
+    cudaStream_t side[2] = {nullptr, nullptr};   // plan-owned side streams / events (plan build + apply_mask run the three
+    cudaEvent_t side_ev[2] = {nullptr, nullptr}, fork_ev = nullptr;  // orders side by side); freed by plan_destroy
     bool masked = false;
     void *ws = nullptr;          // the caller's workspace (cutter temporaries live there)
     int *w_nonunit = nullptr;    // device flag: some bound weight != 1
