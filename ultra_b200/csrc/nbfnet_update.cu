@@ -41,6 +41,13 @@
 // step; 2: issue all four chunks after the last step's barrier (the epilogue covers the latency).  To be A/B-measured.
 #define ULTRA_TC3_PREFETCH 0
 #endif
+#ifndef ULTRA_TC3_L2PF
+// L2 prefetch distance in tiles (0 = off): at the start of tile i one thread asks L2 for the x- and u-rows of tile
+// i + ULTRA_TC3_L2PF with two bulk prefetches (cp.async.bulk.prefetch.L2, 32 KB each, no registers, no shared memory).  The
+// register prefetch of the next tile then hits L2 instead of DRAM, and the DRAM requests of 1 + PF tiles are in flight
+// per SM instead of one - the kernel's limiter is bytes in flight.
+#define ULTRA_TC3_L2PF 0
+#endif
 #ifndef ULTRA_POLL_NS
 #define ULTRA_POLL_NS 64  // sleep between failed mbarrier polls
 #endif
@@ -224,6 +231,16 @@ update_tc3_kernel(const float *__restrict__ x, const float *__restrict__ u, cons
 
     for (int i = 0; i <= n_my; i++) {
         const long long tile = first + (long long)i * step;
+#if ULTRA_TC3_L2PF > 0
+        if (tid < 2) {  // thread 0: x rows, thread 1: u rows of the tile ULTRA_TC3_L2PF ahead
+            const long long pf_row = (tile + (long long)ULTRA_TC3_L2PF * step) * kBM;
+            if (pf_row < M) {
+                const long long rows = (M - pf_row) < kBM ? (M - pf_row) : kBM;
+                const float *src = (tid == 0 ? x : u) + pf_row * kOut;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(rows * kOut * 4)) : "memory");
+            }
+        }
+#endif
         // ================= producer + MMA issue for tile i =========================================================
         if (i < n_my) {
 #pragma unroll
