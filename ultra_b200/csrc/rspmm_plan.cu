@@ -61,10 +61,6 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
         L.w[o] = take((size_t)E * 8);
     }
     L.row_of_edge = take((size_t)E * 4);
-    L.keysA = take((size_t)E * 8);
-    L.keysB = take((size_t)E * 8);
-    L.valsA = take((size_t)E * 4);
-    L.valsB = take((size_t)E * 4);
     L.flags = take(64);  // [0] range error, [1] unsorted, [2] w_nonunit, [4..9] work-queue tickets of the three orders
     L.cub_temp_bytes = (size_t)(1 << 20) + (size_t)E;
     L.cub_temp = take(L.cub_temp_bytes);
@@ -89,6 +85,9 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
         L.seg_ptr_m[o] = take((size_t)(S[o] + 1) * 4);
     }
     L.row_of_edge_m = take((size_t)E * 4);
+    // the edge sorts' key / value double buffers are only alive during plan_build, the masked views only after it:
+    // they share memory (the sort scratch used to stay reserved for the plan's whole life)
+    L.keysA = L.meta_m[0]; L.keysB = L.meta_m[1]; L.valsA = L.eid_m[0]; L.valsB = L.eid_m[1];
     L.total = off;
     return L;
 }
