@@ -3,6 +3,6 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-wl = bench.make_workload(bench.HEADS, "cpu")
+wl = bench.make_workload(bench.HEADS)
 d = torch.device("cuda:0")
-print(bench.bench_layer(wl, d, 1, 0))
+print(bench.bench_layer(wl, d, 1, 0, bench.make_timer(d, 1, None), bench.load_counters()))

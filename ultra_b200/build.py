@@ -30,6 +30,9 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
+    for f in os.listdir(LIB_DIR):  # objects of sources that no longer exist (removed kernels) must not travel with the snapshot
+        if f.endswith(".o") and f.replace(".o", ".cu") not in SOURCES:
+            os.remove(os.path.join(LIB_DIR, f))
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in SOURCES:
