@@ -30,6 +30,9 @@ VARIANTS = {
     "cta1024": {API: ["-DULTRA_CTA_THREADS=1024", "-DULTRA_CTAS_PER_SM=1"]},  # one relation tile per SM -> ~3x the L1
     "cta768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1"]},   # 24 warps, 85 registers, no spills
     "cta768u8": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"]},
+    "pipe768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_PIPE=1"]},
+    "pipe512": {API: ["-DULTRA_FWD_PIPE=1"]},
+    "pipe1024": {API: ["-DULTRA_CTA_THREADS=1024", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_PIPE=1"]},
     "l2pf1": {TC3: ["-DULTRA_TC3_L2PF=1"]},
     "l2pf2": {TC3: ["-DULTRA_TC3_L2PF=2"]},
     "l2pf4": {TC3: ["-DULTRA_TC3_L2PF=4"]},

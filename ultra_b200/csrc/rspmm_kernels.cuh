@@ -39,6 +39,9 @@ namespace ultra {
 #ifndef ULTRA_FWD_UNROLL_W
 #define ULTRA_FWD_UNROLL_W ULTRA_FWD_UNROLL  // same, for the (rare) non-unit-weight path, which also holds U weights per lane
 #endif
+#ifndef ULTRA_FWD_PIPE
+#define ULTRA_FWD_PIPE 0  // experiment: software-pipelined gathers in the forward pass (see walk_items_impl)
+#endif
 #ifndef ULTRA_META_PAIR
 #define ULTRA_META_PAIR 1  // item metadata read two edges at a time (explicit LDS.128); 0 = one LDS.64 per edge
 #endif
@@ -302,6 +305,28 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     }
     __syncwarp();
 
+    // a segment ended inside a whole-segment item: emit the finished row, start the next one
+    auto end_segment = [&]() {
+        if (st_ok) {
+            if (has_bnd && NA == 1) {
+                const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
+#pragma unroll
+                for (int k = 0; k < V; k++) acc[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], bv.v[k]);
+            }
+#pragma unroll
+            for (int a = 0; a < NA; a++)
+                st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes) + (size_t)a * p.dst_plane,
+                          acc[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < NA; a++)
+#pragma unroll
+            for (int k = 0; k < V; k++) acc[a].v[k] = nary_zero_dyn<T>(acc_op(N::red, a));
+        j++;
+        seg = (unsigned)__ldg(p.nonempty + j);  // padded by one entry (0): always a valid row
+        if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
+    };
+
     auto body = [&](auto pred_tag, int i) {
         constexpr bool PRED = decltype(pred_tag)::value;
         int2 m[U];
@@ -411,32 +436,67 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 consume(u);
-                // segment end inside a whole-segment item: emit the finished row, start the next one
-                if (m[u].y < 0 && ok[u]) {
-                    if (st_ok) {
-                        if (has_bnd && NA == 1) {
-                            const Vec<T> bv = ld_row<T>(bnd_c, seg, row_bytes);
-#pragma unroll
-                            for (int k = 0; k < V; k++) acc[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], bv.v[k]);
-                        }
-#pragma unroll
-                        for (int a = 0; a < NA; a++)
-                            st_stream(reinterpret_cast<T *>(dst_c + (unsigned long long)seg * row_bytes) +
-                                          (size_t)a * p.dst_plane, acc[a]);
-                    }
-#pragma unroll
-                    for (int a = 0; a < NA; a++)
-#pragma unroll
-                        for (int k = 0; k < V; k++) acc[a].v[k] = nary_zero_dyn<T>(acc_op(N::red, a));
-                    j++;
-                    seg = (unsigned)__ldg(p.nonempty + j);  // padded by one entry (0): always a valid row
-                    if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
-                }
+                if (m[u].y < 0 && ok[u]) end_segment();
             }
         }
     };
 
     int i = 0;
+#if ULTRA_FWD_PIPE
+    // Experiment (compile-time, off by default): two register stages in the predicate-free part of the forward pass - the
+    // gathers of group g + 1 are issued BEFORE group g is consumed, so a lane keeps 2 * U row gathers in flight instead of
+    // U with a full stop in between.  Needs ~16 more registers than the 64 the 512 x 2 geometry allows (it spills there);
+    // meant for the 768 x 1 geometry (85 registers).  Same arithmetic in the same order: bit-identical results.
+    if constexpr (MODE == FWD && SUM != S_PNA && UNITW && SM == 1 && ULTRA_META_PAIR) {
+        int2 mA[U], mB[U];
+        Vec<T> gA[U], gB[U];
+        auto issue = [&](int2 (&m)[U], Vec<T> (&g)[U], int i0) {
+#pragma unroll
+            for (int u = 0; u < U; u += 2)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(m[u].x), "=r"(m[u].y), "=r"(m[u + 1].x), "=r"(m[u + 1].y)
+                             : "r"(my_meta + (uint32_t)(i0 + u) * 8u));
+#pragma unroll
+            for (int u = 0; u < U; u++) g[u] = ld_row<T>(g1_c, (unsigned)m[u].x, row_bytes);
+        };
+        auto retire = [&](int2 (&m)[U], Vec<T> (&g)[U]) {
+            int any = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) any |= m[u].y;
+            const bool ends = any < 0 && slot == -1;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const Vec<T> rr = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
+#pragma unroll
+                for (int k = 0; k < V; k++)
+                    acc[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], bin_fwd<MUL>(rr.v[k], g[u].v[k]));
+                if (ends && m[u].y < 0) end_segment();
+            }
+        };
+        const int n_full = minlen / U;
+        int g = 0;
+        if (n_full > 0) {
+            issue(mA, gA, 0);
+            while (g + 2 < n_full) {
+                issue(mB, gB, (g + 1) * U);
+                retire(mA, gA);
+                issue(mA, gA, (g + 2) * U);
+                retire(mB, gB);
+                g += 2;
+            }
+            if (g + 1 < n_full) {
+                issue(mB, gB, (g + 1) * U);
+                retire(mA, gA);
+                retire(mB, gB);
+                g += 2;
+            } else {
+                retire(mA, gA);
+                g += 1;
+            }
+        }
+        i = g * U;
+    }
+#endif
     for (; i + U <= minlen; i += U) body(std::false_type{}, i);
     for (; i < maxlen; i += U) body(std::true_type{}, i);
     if (merged) {  // warp-uniform: fold the 4 chunk partials (fixed tree order), the leader stores one slot
