@@ -19,20 +19,3 @@ for heads in (32, 128):
         t4, _ = time_fn(four, iters=5)
         t1, _ = time_fn(one, iters=5)
     print(json.dumps({"heads": heads, "four_calls_ms": round(t4, 3), "one_pass_ms": round(t1, 3), "speedup": round(t4 / t1, 2)}))
-    # backward: four backward calls + autograd of the squares (reference layer) vs ultra_rspmm_backward_pna
-    gs = [torch.randn(N, D, device=d) for _ in range(4)]
-
-    def bwd(fn):
-        r, xx = rel.clone().requires_grad_(), x.clone().requires_grad_()
-        outs = fn(r, xx)
-        torch.autograd.backward(outs, gs)
-    four_b = lambda: bwd(lambda r, xx: (generalized_rspmm(ei, et, w, r, xx, sum="add"),
-                                        generalized_rspmm(ei, et, w, r ** 2, xx ** 2, sum="add"),
-                                        generalized_rspmm(ei, et, w, r, xx, sum="max"),
-                                        generalized_rspmm(ei, et, w, r, xx, sum="min")))
-    one_b = lambda: bwd(lambda r, xx: generalized_rspmm_pna(ei, et, w, r, xx))
-    t4, _ = time_fn(four_b, iters=3)
-    t1, _ = time_fn(one_b, iters=3)
-    print(json.dumps({"heads": heads, "fwd+bwd": True, "four_calls_ms": round(t4, 3), "one_pass_ms": round(t1, 3),
-                      "speedup": round(t4 / t1, 2)}))
-    del gs
