@@ -166,24 +166,11 @@ int ultra_rspmm_backward(const ultra_rspmm_plan *plan, int sum_op, int mul_op, i
  * (/root/reference/ultra/layers.py:211-215: sum, sum over (relation**2, input**2), max, min); this entry point
  * gathers every row slice once and produces all four.  output4 is (4, num_node, dim): [0] sum, [1] sum of squares,
  * [2] max, [3] min, each exactly what the corresponding ultra_rspmm_forward call would write.  scratch must hold
- * 4 * ultra_rspmm_scratch_bytes(plan, dim, dtype).  Gradients: ultra_rspmm_backward_pna.
+ * 4 * ultra_rspmm_scratch_bytes(plan, dim, dtype).  Forward only: gradients compose from the four backward calls.
  */
 int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype, const void *relation,
                             const void *input, void *output4, int64_t dim, void *scratch, size_t scratch_bytes,
                             void *stream);
-
-/*
- * Backward of the one-pass PNA aggregation, also in one pass per gradient: output4 / output_grad4 are (4, num_node, dim)
- * in the order of ultra_rspmm_forward_pna.  Per edge the by-column pass gathers the four output_grad slices and the max /
- * min outputs of the aggregating node ONCE and accumulates
- *     w * ( (g_sum + g_max [y == max] + g_min [y == min]) * dx/d input  +  g_sq * d(rel^2 (x) in^2)/d input )
- * into input_grad; the by-relation pass does the same for relation_grad.  The reference reaches these gradients through
- * four backward calls plus the autograd of `relation ** 2`, `input ** 2` (/root/reference/ultra/layers.py:211-215).
- * No weight_grad here (callers that need it compose it from the four ultra_rspmm_backward calls).
- */
-int ultra_rspmm_backward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype, const void *relation,
-                             const void *input, const void *output4, const void *output_grad4, void *relation_grad,
-                             void *input_grad, int64_t dim, void *scratch, size_t scratch_bytes, void *stream);
 
 /*
  * Head-major variants: the NBFNet layer keeps its state as (num_heads, rows, head_dim) = (B, N, d); the reference

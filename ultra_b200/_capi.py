@@ -32,7 +32,6 @@ SYMBOLS = {
     "ultra_rspmm_forward": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_backward": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_forward_pna": (_int, [_vp, _int, _int, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
-    "ultra_rspmm_backward_pna": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "ultra_rspmm_forward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp, _sz, _vp]),
     "ultra_rspmm_backward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp,
                                           _sz, _vp]),

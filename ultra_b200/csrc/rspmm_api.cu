@@ -103,7 +103,6 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     const int ub_warp_items = so.num_items / kSubPerWarp;  // exact for the base graph, an upper bound under an edge mask
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
     p.dst = dst; p.rgrad = rgrad; p.partial = scratch; p.boundary = boundary; p.lay = lay;
-    p.in_plane = (long long)plan->N * D;                          // S_PNA backward: (4, N, D) output / output_grad
     p.dst_plane = (long long)plan->ord[ORD].num_seg * D;          // S_PNA: (4, N, D) outputs
     p.partial_plane = (long long)plan->ord[ORD].num_slots * D;    // S_PNA: (4, slots, D) partials
     p.D = (int)D; p.R = (int)plan->R; p.N = (int)plan->N;
@@ -492,33 +491,6 @@ int ultra_rspmm_forward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype,
     }
     if (mul_op == 0) return forward_t<double, S_PNA, M_MUL>(plan, relation, input, output4, dim, scratch, stream);
     return forward_t<double, S_PNA, M_ADD>(plan, relation, input, output4, dim, scratch, stream);
-}
-
-int ultra_rspmm_backward_pna(const ultra_rspmm_plan *plan, int mul_op, int dtype, const void *relation,
-                             const void *input, const void *output4, const void *output_grad4, void *relation_grad,
-                             void *input_grad, int64_t dim, void *scratch, size_t scratch_bytes_, void *stream_) {
-    if (int rc = check_common(plan, 0, mul_op, dtype, dim)) return rc;
-    if (scratch_bytes_ < scratch_bytes(plan, dim, dtype)) { set_error("backward_pna: scratch too small"); return 1; }
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    auto run = [&](auto tag, auto mul_tag) -> int {
-        using T = decltype(tag);
-        constexpr int MUL = decltype(mul_tag)::value;
-        if (!vec_ok<T>(dim, {relation, input, output4, output_grad4, relation_grad, input_grad, scratch})) {
-            set_error("backward_pna needs the vector path (D % 4 == 0, 16-byte aligned pointers)");
-            return 1;
-        }
-        if (int rc = launch_pass<T, BWD_IN, S_PNA, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output4,
-                                                        (const T *)output_grad4, (T *)input_grad, (T *)scratch, dim, stream))
-            return rc;
-        return launch_pass<T, BWD_REL, S_PNA, MUL>(plan, (const T *)relation, (const T *)input, (const T *)output4,
-                                                   (const T *)output_grad4, (T *)relation_grad, (T *)scratch, dim, stream);
-    };
-    if (dtype == ULTRA_RSPMM_F32) {
-        if (mul_op == 0) return run(float{}, std::integral_constant<int, M_MUL>{});
-        return run(float{}, std::integral_constant<int, M_ADD>{});
-    }
-    if (mul_op == 0) return run(double{}, std::integral_constant<int, M_MUL>{});
-    return run(double{}, std::integral_constant<int, M_ADD>{});
 }
 
 int ultra_rspmm_forward_heads(const ultra_rspmm_plan *plan, int sum_op, int mul_op, int dtype, const void *relation,

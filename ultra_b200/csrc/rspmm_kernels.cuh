@@ -188,7 +188,6 @@ template <typename T> struct SegParams {
     T *partial;         // (num_slots, D), always flat
     long long dst_plane;      // S_PNA: element stride between the 4 output matrices (sum, sq_sum, max, min)
     long long partial_plane;  // S_PNA: element stride between the 4 partial buffers
-    long long in_plane;       // S_PNA backward: element stride between the 4 output / output_grad matrices
     const T *boundary;  // forward only, optional: out = Nary(agg, boundary) (the NBFNet self-loop message); dst layout
     Layout lay;         // where tile t / row r of the feature matrices live (flat (rows, D) or head-major (B, rows, d))
     int D;
@@ -267,11 +266,7 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     const int2 *mp = p.meta + e0;
     const T *wp = UNITW ? nullptr : p.w + e0;
     const char *g1_c = reinterpret_cast<const char *>(MODE == FWD ? p.input : p.outgrad) + off_n;
-    // one-pass PNA backward (SUM == S_PNA, MODE != FWD): output_grad is (4, N, D) = d/d(sum, sq_sum, max, min), output is
-    // (4, N, D); the tie masks need planes 2 (max) and 3 (min) of output
-    constexpr bool kPnaBwd = (MODE != FWD) && SUM == S_PNA;
-    const size_t pna_plane = kPnaBwd ? (size_t)p.in_plane * sizeof(T) : 0;
-    const char *out_c = reinterpret_cast<const char *>(p.output) + off_n + 2 * pna_plane;
+    const char *out_c = reinterpret_cast<const char *>(p.output) + off_n;
     const char *in_c = reinterpret_cast<const char *>(p.input) + off_n;
     const char *rel_c = reinterpret_cast<const char *>(p.relation) + off_r;
     const char *self_c = by_col(MODE) ? in_c : rel_c;
@@ -368,16 +363,6 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             if (N::out) g2[u] = ld_row<T>(out_c, (unsigned)m[u].x, row_bytes);
             if (N::inb) g3[u] = ld_row<T>(in_c, (unsigned)m[u].y & 0x7fffffffu, row_bytes);
         }
-        Vec<T> gq[U], gmx[U], gmn[U], omn[U];  // PNA backward: output_grad planes 1..3 and output plane 3 (g1 / g2 hold 0 / 2)
-        if (kPnaBwd) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                gq[u] = ld_row<T>(g1_c + pna_plane, (unsigned)m[u].x, row_bytes);
-                gmx[u] = ld_row<T>(g1_c + 2 * pna_plane, (unsigned)m[u].x, row_bytes);
-                gmn[u] = ld_row<T>(g1_c + 3 * pna_plane, (unsigned)m[u].x, row_bytes);
-                omn[u] = ld_row<T>(out_c + pna_plane, (unsigned)m[u].x, row_bytes);
-            }
-        }
         Vec<T> rr[U];
         if (N::rel && !REL_SMEM) {  // relation rows from L1/L2: issue all loads up front (long latency)
 #pragma unroll
@@ -406,23 +391,6 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
                     } else {
                         nxt[0].v[k] = nary_fwd_dyn<T>(N::red, acc[0].v[k], y);
                     }
-                } else if (kPnaBwd) {
-                    // all four PNA aggregates at once (layers.py:211-215): per edge
-                    //   d = w * ( (g_sum + g_max [y == max] + g_min [y == min]) * dx/d. + g_sq * d(rel^2 (x) in^2)/d. )
-                    // by-col pass: d/d in (segment = col, self = input[col]); by-relation pass: d/d rel (self = relation[type])
-                    const T r = by_col(MODE) ? rr[u].v[k] : self.v[k];
-                    const T xin = by_col(MODE) ? self.v[k] : g3[u].v[k];
-                    T y = bin_fwd<MUL>(r, xin);
-                    if (!UNITW) y = wv[u] * y;
-                    const T G = g1[u].v[k] + gmx[u].v[k] * nary_bwd<S_MAX>(g2[u].v[k], y) +
-                                gmn[u].v[k] * nary_bwd<S_MIN>(omn[u].v[k], y);
-                    const T other = by_col(MODE) ? r : xin;  // d x / d (the operand we differentiate) for mul
-                    const T mine = by_col(MODE) ? xin : r;
-                    const T d1 = MUL == M_MUL ? other : T(1);
-                    const T d2 = MUL == M_MUL ? T(2) * other * other * mine : T(2) * mine;
-                    T g = G * d1 + gq[u].v[k] * d2;
-                    if (!UNITW) g = g * wv[u];
-                    nxt[0].v[k] = acc[0].v[k] + g;
                 } else if (by_col(MODE)) {
                     // rspmm.cu:198-209  input_grad[col] += og * dout_dy * w * dx_din ; segment = col
                     T g = g1[u].v[k];

@@ -3,9 +3,7 @@
 The reference layer issues FOUR rspmm calls over the same edges for `aggregate_func == "pna"`
 (/root/reference/ultra/layers.py:211-215): sum, sum over (relation**2, input**2), max, min.
 `generalized_rspmm_pna` gathers every input row slice once and returns all four (ultra_rspmm_forward_pna).
-Gradients: ultra_rspmm_backward_pna, again one gather pass per gradient (the four output_grad slices and the max / min
-outputs of a node are fetched once per edge); only when edge_weight needs a gradient they compose from the four existing
-backward kernels.
+Gradients compose from the four existing backward kernels (same cost as the reference's four backward calls).
 """
 import torch
 from torch import autograd
@@ -50,19 +48,6 @@ class RSPMMPnaFunction(autograd.Function):
         plan.bind_weight(edge_weight)
         need_wg = ctx.needs_input_grad[2]
         z = lambda g: torch.zeros_like(x) if g is None else g.contiguous()
-        if not need_wg:
-            lib = _capi.lib()
-            og4 = torch.stack([z(g_sum), z(g_sq), z(g_max), z(g_min)])
-            relation_grad, input_grad = torch.empty_like(rel), torch.empty_like(x)
-            dim = x.size(1)
-            scratch = plan.scratch(dim, x.dtype)
-            with torch.cuda.device(x.device):
-                rc = lib.ultra_rspmm_backward_pna(plan.handle, ctx.mul_id, _DTYPE_ID[x.dtype], rel.data_ptr(), x.data_ptr(),
-                                                  out4.data_ptr(), og4.data_ptr(), relation_grad.data_ptr(),
-                                                  input_grad.data_ptr(), dim, scratch.data_ptr(), scratch.numel(),
-                                                  _stream_ptr(x.device))
-            _capi.check(rc, "ultra_rspmm_backward_pna")
-            return None, None, None, relation_grad, input_grad, None
         ADD, MIN, MAX = _capi.SUM_IDS["add"], _capi.SUM_IDS["min"], _capi.SUM_IDS["max"]
         run = lambda s, r, i, o, g: _run_backward(plan, s, ctx.mul_id, r, i, o, g, need_wg, ctx.num_edge)
         wg1, rg1, ig1 = run(ADD, rel, x, out4[0], z(g_sum))
