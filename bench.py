@@ -608,6 +608,33 @@ def bench_layer(wl, device, world, rank, timeit, counters):
         info["training_layer_error"] = repr(exc)
     del layers, x, bd, u
     torch.cuda.empty_cache()
+    # a whole TRAINING step of the 6-layer entity stack (forward + backward, this step's easy edges removed through the
+    # incremental plan: ultra_rspmm_plan_apply_mask, no sort, no host sync), 32 heads
+    try:
+        from ultra_b200.nbfnet import UltraNBFNet
+        torch.manual_seed(9)
+        model = UltraNBFNet().to(device).train()
+        Bt = 32
+        rel_t = torch.randn(Bt, R, d, device=device, requires_grad=True)
+        h_t = torch.randint(0, N, (Bt,), device=device)
+        r_t = torch.randint(0, R // 2, (Bt,), device=device)
+        t_t = torch.randint(0, N, (Bt,), device=device)
+        keep = UltraNBFNet.easy_edge_mask(ei, et, N, R, h_t, t_t, r_t)
+
+        def train_stack():
+            model.zero_grad(set_to_none=True)
+            rel_t.grad = None
+            hidden, _ = model.entity_states(ei, et, N, rel_t, h_t, r_t, edge_mask=keep)
+            hidden.square().mean().backward()
+        info["training_stack6_ms"] = timeit(train_stack, reps=3, warm=2)
+        info["training_stack6_what"] = ("6-layer entity stack, forward + backward, %d heads, per-step edge mask applied through the "
+                                        "incremental plan (%d of %d edges removed)" % (Bt, int((~keep).sum()), ei.shape[1]))
+        from ultra_b200.plan import plan_cache
+        plan_cache.get(ei, et, N, R).apply_edge_mask(None)
+        del model, rel_t
+    except Exception as exc:  # noqa: BLE001 - extras only
+        info["training_stack6_error"] = repr(exc)
+    torch.cuda.empty_cache()
     return info
 
 

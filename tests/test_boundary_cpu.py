@@ -132,3 +132,12 @@ def test_plain_c_consumer(capi, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
     assert r.stdout.startswith("ultra_rspmm sm_100a")
+
+
+def test_numa_cpulist_parsing_and_graceful_fallback():
+    """ultra_b200.numa: sysfs cpulist syntax; on a box without GPU / NUMA information the pinning is a no-op, not an error."""
+    from ultra_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set() and numa._parse_cpulist(None) == set()
+    info = numa.pin_to_gpu_numa(0)
+    assert "node" in info
