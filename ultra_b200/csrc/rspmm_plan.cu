@@ -27,6 +27,7 @@ constexpr size_t kAlign = 256;
 constexpr int kCutBlock = 64;    // segments per cutter thread (see cut_walk_block)
 constexpr int kPlanCounts = 8;   // ints per order in the device-side result block (cut_finalize_kernel)
 struct CutCounts { int whole, groups, chunks, slots, nlong, nempty, nonempty; };  // per cutter block / running totals
+struct LongRec { int seg, b, e, j, slot0, group0, chunk0, pad; };  // a long segment + where its items / slots go
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 inline int bits_for(int64_t n) {  // bits needed to represent values in [0, n)
     int b = 1;
@@ -41,7 +42,7 @@ struct WsLayout {
     size_t meta[3], eid[3], seg_ptr[3], nonempty[3], items[3], fix[3], w[3];
     size_t row_of_edge, keysA, keysB, valsA, valsB, flags, cub_temp, cub_temp_bytes, total;
     // device cutter / mask temporaries, one set PER ORDER (the three orders are processed on three streams), + result counts
-    size_t cut_cnt[3], cut_incl[3], rkeys[3][2], ritems[3][2], cut_temp[3], cut_temp_bytes, counts;
+    size_t cut_cnt[3], cut_incl[3], rkeys[3][2], ritems[3][2], cut_temp[3], cut_temp_bytes, counts, longs[3];
     size_t meta_m[3], eid_m[3], seg_ptr_m[3], row_of_edge_m, mask_pos[3];  // masked views (plan_apply_mask)
     int64_t max_blocks, rest_cap;
 };
@@ -76,6 +77,7 @@ WsLayout make_layout(int64_t N, int64_t E, int64_t R) {
             L.ritems[o][k] = take((size_t)L.rest_cap * 16);
         }
         L.cut_temp[o] = take(L.cut_temp_bytes);
+        L.longs[o] = take((size_t)std::min<int64_t>(S[o], E / (kItemEdges + 1) + 1) * sizeof(LongRec));
         L.mask_pos[o] = take((size_t)E * 4);
     }
     L.counts = take(3 * kPlanCounts * sizeof(int));
@@ -225,6 +227,7 @@ struct WriteVisitor {
     int4 *ritems;       // whole-segment items [0, tot.whole), single chunks [tot.whole, tot.whole + tot.chunks)
     int4 *fix;
     int *nonempty_out;
+    LongRec *longs;
     int w = 0, g = 0, c = 0, sl = 0, l = 0, em = 0, ne = 0;
     __host__ __device__ void empty(int s) { fix[tot.nlong + off.nempty + em++] = make_int4(s, 0, 0, 0); }
     __host__ __device__ void nonempty(int s) { nonempty_out[off.nonempty + ne++] = s; }
@@ -234,25 +237,41 @@ struct WriteVisitor {
         rkeys[i] = rest_key(e0, e1);
     }
     __host__ __device__ void long_seg(int s, int b, int e, int j) {
-        const int jj = off.nonempty + j, slot0 = off.slots + sl;
-        const int kGroup = kItemEdges * kSubPerWarp;
-        int cpos = b, k = 0;
-        for (; cpos + kGroup <= e; cpos += kGroup, k++) {
-            const int gi = off.groups + g++;
-            for (int t = 0; t < kSubPerWarp; t++)
-                items[(size_t)gi * kSubPerWarp + t] = make_int4(cpos + t * kItemEdges, cpos + (t + 1) * kItemEdges,
-                                                                jj | kMergedBit, t ? -2 : slot0 + k);
-        }
-        for (; cpos < e; cpos += kItemEdges, k++) {
-            const int i = tot.whole + off.chunks + c++;
-            const int e1 = cpos + kItemEdges < e ? cpos + kItemEdges : e;
-            ritems[i] = make_int4(cpos, e1, jj, slot0 + k);
-            rkeys[i] = rest_key(cpos, e1);
-        }
-        fix[off.nlong + l++] = make_int4(s, slot0, k, 0);
-        sl += k;
+        // only the bookkeeping here: the segment's chunk / group items are written by emit_long, one CTA per long
+        // segment (a hub row of 10^5 edges is thousands of items - far too many for the one thread that walks this block)
+        const int deg = e - b, groups = deg / (kItemEdges * kSubPerWarp);
+        const int rest = (deg - groups * kItemEdges * kSubPerWarp + kItemEdges - 1) / kItemEdges;
+        const int slot0 = off.slots + sl;
+        longs[off.nlong + l] = LongRec{s, b, e, off.nonempty + j, slot0, off.groups + g, off.chunks + c, 0};
+        fix[off.nlong + l] = make_int4(s, slot0, groups + rest, 0);
+        l++; sl += groups + rest; g += groups; c += rest;
     }
 };
+
+// items of one long segment; thread t of nt (device: a CTA per segment; host mirror: t = 0, nt = 1)
+__host__ __device__ inline void emit_long(const LongRec &r, const CutCounts &tot, int4 *items, unsigned long long *rkeys,
+                                          int4 *ritems, int t, int nt) {
+    const int kGroup = kItemEdges * kSubPerWarp;
+    const int groups = (r.e - r.b) / kGroup;
+    for (int k = t; k < groups * kSubPerWarp; k += nt) {
+        const int gi = k / kSubPerWarp, tt = k % kSubPerWarp, cpos = r.b + gi * kGroup;
+        items[(size_t)(r.group0 + gi) * kSubPerWarp + tt] =
+            make_int4(cpos + tt * kItemEdges, cpos + (tt + 1) * kItemEdges, r.j | kMergedBit, tt ? -2 : r.slot0 + gi);
+    }
+    const int cstart = r.b + groups * kGroup, rest = (r.e - cstart + kItemEdges - 1) / kItemEdges;
+    for (int k = t; k < rest; k += nt) {
+        const int cpos = cstart + k * kItemEdges, e1 = cpos + kItemEdges < r.e ? cpos + kItemEdges : r.e;
+        const int i = tot.whole + r.chunk0 + k;
+        ritems[i] = make_int4(cpos, e1, r.j, r.slot0 + groups + k);
+        rkeys[i] = rest_key(cpos, e1);
+    }
+}
+
+__global__ void cut_long_kernel(const LongRec *__restrict__ longs, const CutCounts *__restrict__ incl, int nb, int4 *items,
+                                unsigned long long *rkeys, int4 *ritems) {
+    const CutCounts tot = incl[nb - 1];
+    for (int li = blockIdx.x; li < tot.nlong; li += gridDim.x) emit_long(longs[li], tot, items, rkeys, ritems, threadIdx.x, blockDim.x);
+}
 
 __global__ void cut_count_kernel(const int *__restrict__ ptr, int S, CutCounts *__restrict__ cnt, int nb) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,10 +283,12 @@ __global__ void cut_count_kernel(const int *__restrict__ ptr, int S, CutCounts *
 }
 
 __global__ void cut_write_kernel(const int *__restrict__ ptr, int S, const CutCounts *__restrict__ incl, int nb,
-                                 int4 *items, unsigned long long *rkeys, int4 *ritems, int4 *fix, int *nonempty) {
+                                 int4 *items, unsigned long long *rkeys, int4 *ritems, int4 *fix, int *nonempty,
+                                 LongRec *longs) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     WriteVisitor v;
+    v.longs = longs;
     v.off = b ? incl[b - 1] : CutCounts{0, 0, 0, 0, 0, 0, 0};
     v.tot = incl[nb - 1];
     v.items = items; v.rkeys = rkeys; v.ritems = ritems; v.fix = fix; v.nonempty_out = nonempty;
@@ -346,8 +367,13 @@ int cut_items_device(int o, const int *seg_ptr, int S, int64_t E, const WsLayout
     temp_bytes = L.cut_temp_bytes;
     CUDA_TRY(cub::DeviceScan::InclusiveScan(ws + L.cut_temp[o], temp_bytes, cnt, incl, CutSum(), nb, stream));
     CUDA_TRY(cudaMemsetAsync(dk.Current(), 0xff, (size_t)cap * 8, stream));  // unused entries sort to the end
+    auto *longs = reinterpret_cast<LongRec *>(ws + L.longs[o]);
     cut_write_kernel<<<blocks, threads, 0, stream>>>(seg_ptr, S, incl, nb, so.items, dk.Current(), dv.Current(), so.fix,
-                                                     so.nonempty);
+                                                     so.nonempty, longs);
+    CUDA_TRY(cudaGetLastError());
+    const int long_ub = (int)std::min<int64_t>(S, E / (kItemEdges + 1) + 1);  // the exact count lives in incl[nb - 1]
+    cut_long_kernel<<<std::max(1, std::min(long_ub, 592)), 128, 0, stream>>>(longs, incl, nb, so.items, dk.Current(),
+                                                                             dv.Current());
     CUDA_TRY(cudaGetLastError());
     temp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, cap, 0, 39, stream));
@@ -388,8 +414,10 @@ int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t item
     }
     std::vector<int4> ritems(std::max(rest, 1));
     std::vector<unsigned long long> rkeys(std::max(rest, 1));
+    std::vector<LongRec> longs(std::max(tot.nlong, 1));
     for (int b = 0; b < nb; b++) {
         WriteVisitor v;
+        v.longs = longs.data();
         v.off = b ? incl[b - 1] : CutCounts{0, 0, 0, 0, 0, 0, 0};
         v.tot = tot;
         v.items = reinterpret_cast<int4 *>(items_out); v.rkeys = rkeys.data(); v.ritems = ritems.data();
@@ -397,6 +425,8 @@ int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t item
         const int s0 = b * kCutBlock, s1 = std::min(S, s0 + kCutBlock);
         if (s0 < s1) cut_walk_block(seg_ptr, s0, s1, v);
     }
+    for (int li = 0; li < tot.nlong; li++)
+        emit_long(longs[li], tot, reinterpret_cast<int4 *>(items_out), rkeys.data(), ritems.data(), 0, 1);
     std::vector<int> order(rest);
     for (int i = 0; i < rest; i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return rkeys[a] < rkeys[b]; });  // keys are distinct
