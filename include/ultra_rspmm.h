@@ -16,6 +16,9 @@
  *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*); forward/backward
  *     never synchronise the host and are CUDA-graph capturable.  plan_build synchronises `stream` exactly once, at its
  *     end (sorts, CSR construction and the work-item cutter all run on the device).
+ *   - a plan is a single-stream object: calls that use the same plan must be stream-ordered with respect to each other
+ *     (the plan's workspace holds the bound weights, the work-queue tickets of the persistent kernels and, under an edge
+ *     mask, the active edge arrays).  Different plans are independent; there is no process-global launch state.
  *   - dtype: ULTRA_RSPMM_F32 or ULTRA_RSPMM_F64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES,
  *     rspmm.cu:251,313,332).  Indices are int64 at the boundary (reference convention, rspmm.cpp:22),
  *     int32 inside the plan.
@@ -45,6 +48,8 @@ const char *ultra_rspmm_version(void);
 /*
  * Process-wide launch tunables (experiment knobs; nothing on the data path depends on them being set).
  * "l2_percent": share of L2 (default 25) the concurrently gathered input tiles may occupy (tile-major schedule).
+ * "smem_tiles": highest shared-memory residency mode the segment kernel may choose (2 = relation tile + gathered tile for
+ * small graphs, 1 = relation tile only, 0 = none; default 2) - an experiment knob (0 costs +13 % at FB15k-237 scale).
  * "host_copy_split": row blocks per slab copy in forward_host.
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a
