@@ -153,3 +153,55 @@ def test_apply_mask_forward_backward_capture_as_one_cuda_graph(cuda_device):
             assert_close_ref(g_rg, e_rg, "replayed masked relation_grad")
     finally:
         plan.apply_edge_mask(None)
+
+
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.float64, 16)])
+def test_masked_plan_head_major_and_fp64(cuda_device, dtype, d):
+    """The head-major entry points (the layer's native (B, N, d) layout, boundary folded) and fp64 under an edge mask:
+    bit-identical to the same call on the filtered edge list."""
+    from ultra_b200.fused import rspmm_heads
+    from ultra_b200.plan import plan_cache
+    dev = cuda_device
+    g = torch.Generator().manual_seed(91)
+    B, N, R, E = 4, 150, 6, 6000
+    ei = torch.randint(0, N - 2, (2, E), generator=g)
+    ei[0, :1500] = 3
+    et = torch.randint(0, R, (E,), generator=g)
+    rel = torch.randn(B, R, d, generator=g, dtype=dtype).to(dev)
+    x = torch.randn(B, N, d, generator=g, dtype=dtype).to(dev)
+    bd = torch.randn(B, N, d, generator=g, dtype=dtype).to(dev)
+    og = torch.randn(B, N, d, generator=g, dtype=dtype).to(dev)
+    eid, etd = ei.to(dev), et.to(dev)
+    w = torch.ones(E, dtype=dtype, device=dev)
+    keep = _mask(E, 7, 0.25, dev, ei)
+
+    def run(e_i, e_t, ww, sum):
+        r, xx = rel.clone().requires_grad_(), x.clone().requires_grad_()
+        out = rspmm_heads(e_i, e_t, ww, r, xx, bd, sum=sum, mul="mul")
+        out.backward(og)
+        return out.detach(), r.grad, xx.grad
+    plan = plan_cache.get(eid, etd, N, R)
+    for sum in ("add", "max"):
+        plan.apply_edge_mask(keep)
+        try:
+            got = run(eid, etd, w, sum)
+        finally:
+            plan.apply_edge_mask(None)
+        exp = run(eid[:, keep].contiguous(), etd[keep].contiguous(), torch.ones(int(keep.sum()), dtype=dtype, device=dev), sum)
+        for a, b in zip(got, exp):
+            assert torch.equal(a, b)
+
+
+def test_plan_cache_is_bounded_by_bytes(cuda_device):
+    """a caller that hands a fresh edge tensor to every call (the reference's training loop) must not pin an
+    unbounded number of stale plan workspaces: the LRU evicts by device bytes as well as by entries."""
+    from ultra_b200.plan import PlanCache
+    dev = cuda_device
+    cache = PlanCache(capacity=64, max_bytes=40 << 20)
+    g = torch.Generator().manual_seed(92)
+    for _ in range(12):
+        ei = torch.randint(0, 2000, (2, 60000), generator=g).to(dev)   # a new tensor every time: ~9 MB of workspace each
+        et = torch.randint(0, 10, (60000,), generator=g).to(dev)
+        cache.get(ei, et, 2000, 10)
+    total = sum(e[0].nbytes() for e in cache._entries.values())
+    assert cache.misses == 12 and 1 <= len(cache._entries) < 12 and total <= (40 << 20) + (12 << 20)
