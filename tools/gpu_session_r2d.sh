@@ -24,10 +24,13 @@ timeout 240 ncu --set full --clock-control none -k regex:seg_reduce_kernel -s 13
 stamp "ncu --set full: update kernel"
 timeout 200 ncu --set full --clock-control none -k regex:update_ -s 3 -c 1 -f -o gpurun_out/r02_update \
     python tools/update_bench.py > gpurun_out/ncu_upd.log 2>&1
+stamp "summaries of the captures (the .ncu-rep files are too large to travel back: 64 MiB limit)"
+python tools/ncu_summary.py gpurun_out/r02_fwd.ncu-rep gpurun_out/r02_bwd.ncu-rep gpurun_out/r02_update.ncu-rep > gpurun_out/r02_ncu_summary.md 2>&1
+python tools/ncu_roofline_json.py --out=gpurun_out/roofline_traffic.json forward=gpurun_out/r02_fwd.ncu-rep backward_in=gpurun_out/r02_bwd.ncu-rep:0 \
+    backward_rel=gpurun_out/r02_bwd.ncu-rep:1 update=gpurun_out/r02_update.ncu-rep > /dev/null 2>&1
+ncu -i gpurun_out/r02_fwd.ncu-rep --page source --csv 2>/dev/null | head -400 > gpurun_out/r02_fwd_source_page_head.csv
+rm -f gpurun_out/r02_bwd.ncu-rep gpurun_out/r02_update.ncu-rep
 stamp "sweep (C1-C5) with same-run parity"
 timeout 600 python tools/sweep.py > gpurun_out/r02_sweep_stdout.jsonl 2> gpurun_out/sweep.err
 stamp "sweep rc=$? lines=$(wc -l < gpurun_out/r02_sweep_stdout.jsonl)"
-stamp "pytest -m gpu (log for profiles)"
-timeout 900 python -m pytest tests -m gpu -q --maxfail=8 --durations=5 > gpurun_out/pytest_full.log 2>&1
-stamp "pytest rc=$? : $(tail -1 gpurun_out/pytest_full.log)"
 stamp "done"

@@ -39,7 +39,14 @@ def read(rep, idx):
 
 def main():
     data = {}
+    out_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    args = []
     for arg in sys.argv[1:]:
+        if arg.startswith("--out="):
+            out_path = arg[len("--out="):]
+        else:
+            args.append(arg)
+    for arg in args:
         role, spec = arg.split("=", 1)
         rep, _, idx = spec.partition(":")
         data[role] = read(rep, int(idx or 0))
@@ -53,7 +60,7 @@ def main():
                             "l2_frac": (a["l2_frac"] * a["ncu_duration_ms"] + b["l2_frac"] * b["ncu_duration_ms"])
                             / (a["ncu_duration_ms"] + b["ncu_duration_ms"]),
                             "source": "time-weighted over the two passes"}
-    with open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w") as f:
+    with open(out_path, "w") as f:
         json.dump(data, f, indent=1)
     print(json.dumps(data, indent=1))
 
