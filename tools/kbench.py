@@ -38,12 +38,15 @@ def main():
     ap.add_argument("--peak", type=float, default=6583.2)
     ap.add_argument("--l2-percent", type=int, default=0)
     ap.add_argument("--sm-limit", type=int, default=0)
+    ap.add_argument("--work-queue", type=int, default=-1, help="experiment: 1 ticket work queue (default), 0 static round-robin")
     ap.add_argument("--smem-tiles", type=int, default=-1, help="experiment: highest smem residency mode (2 / 1 / 0)")
     ap.add_argument("--mask-frac", type=float, default=0.0,
                     help="bind a 0/1 edge weight that removes this fraction of the edges (the weighted kernel path)")
     args = ap.parse_args()
     d = torch.device("cuda:0")
     lib = _capi.lib()
+    if args.work_queue >= 0:
+        _capi.set_tunable("work_queue", args.work_queue)
     if args.smem_tiles >= 0:
         _capi.set_tunable("smem_tiles", args.smem_tiles)
     if args.l2_percent:

@@ -35,6 +35,7 @@ static_assert(kCtasPerSm != 2 || kCtaThreads != 512 || kSlabSmemLimit == 78 * 10
 std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
 std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy
 std::atomic<int> g_bwd_fused_relgrad{0};
+std::atomic<int> g_work_queue{1};       // experiment knob: 1 = ticket work queue (default), 0 = static round-robin
 std::atomic<int> g_smem_tiles{2};       // experiment knob: highest SM mode allowed (2 all, 1 relation tile only, 0 none) // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
 
 template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *> ptrs) {
@@ -98,7 +99,7 @@ int launch_pass(const ultra_rspmm_plan *plan, const T *relation, const T *input,
     }
 
     SegParams<T> p;
-    p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.sched = plan->sched + 2 * ORD; p.nonempty = so.nonempty; p.items = so.items;
+    p.meta = so.meta; p.w = w; p.w_nonunit = plan->w_nonunit; p.sched = g_work_queue.load() ? plan->sched + 2 * ORD : nullptr; p.nonempty = so.nonempty; p.items = so.items;
     p.counts = so.counts;
     const int ub_warp_items = so.num_items / kSubPerWarp;  // exact for the base graph, an upper bound under an edge mask
     p.relation = relation; p.input = input; p.output = output; p.outgrad = outgrad;
@@ -327,9 +328,10 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     const std::string n(name);
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
+    if (n == "work_queue") { g_work_queue.store(value != 0); return 0; }
     if (n == "smem_tiles") { g_smem_tiles.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, smem_tiles)");
+    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, smem_tiles, work_queue)");
     return 1;
 }
 

@@ -598,14 +598,20 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
     const int num_warp_items = __ldg(p.counts) / kSubPerWarp;
     const int units_per_tile = (num_warp_items + kCtaWarps * p.items_per_warp - 1) / (kCtaWarps * p.items_per_warp);
     const long long total_units = (long long)units_per_tile * p.num_tiles;
+    // p.sched == nullptr selects a static round-robin (blocks blockIdx.x, + gridDim.x, ...; tunable "work_queue" = 0), kept
+    // for A/B runs only: without the queue the CTAs drift apart, the window of active tiles outgrows its L2 budget and the
+    // forward pass re-reads 3x the compulsory bytes from DRAM (2.35 vs 1.96 ms at C2, profiles/r02_work_queue_ab.txt)
+    const bool dynamic = p.sched != nullptr;
     __shared__ int s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
-    __syncthreads();
+    if (dynamic) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.sched, 1);
+        __syncthreads();
+    }
+    long long blk = dynamic ? (long long)s_ticket : (long long)blockIdx.x;
     for (;;) {
-        const long long blk = s_ticket;
         if (blk * p.run >= total_units) break;
         int next_ticket = 0;
-        if (threadIdx.x == 0) next_ticket = atomicAdd(p.sched, 1);  // consumed only after the block (no stall here)
+        if (dynamic && threadIdx.x == 0) next_ticket = atomicAdd(p.sched, 1);  // consumed only after the block (no stall here)
         for (int uu = 0; uu < p.run; uu++) {
             const long long unit = blk * p.run + uu;
             if (unit >= total_units) break;
@@ -646,12 +652,17 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) seg_reduce_kernel(con
                 if (wi < num_warp_items) walk_items<T, MODE, SUM, MUL, SM>(p, wi, tile, rel_s_addr, g1_s_addr, meta_s_addr, use_w);
             }
         }
-        __syncthreads();  // every thread has read this block's ticket
-        if (threadIdx.x == 0) s_ticket = next_ticket;
-        __syncthreads();
+        if (dynamic) {
+            __syncthreads();  // every thread has read this block's ticket
+            if (threadIdx.x == 0) s_ticket = next_ticket;
+            __syncthreads();
+            blk = s_ticket;
+        } else {
+            blk += gridDim.x;
+        }
     }
     // the last CTA to leave resets the queue for the next launch on this plan (launches of one plan are stream-ordered)
-    if (threadIdx.x == 0) {
+    if (dynamic && threadIdx.x == 0) {
         if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
             p.sched[0] = 0;
             p.sched[1] = 0;
