@@ -22,7 +22,7 @@ from ultra_b200 import build as lib_build  # noqa: E402
 #    so it needs the clamped single loads (PAIR=0).
 #  * BF16x3 layer epilogue: where the next tile's loads are issued (ULTRA_TC3_PREFETCH, see nbfnet_update.cu): the
 #    ncu source page shows the membar of fence.proxy.async waiting for the loads issued just before it.
-API, TC3 = "rspmm_api.cu", "nbfnet_update.cu"
+API, TC3, PLAN = "rspmm_api.cu", "nbfnet_update.cu", "rspmm_plan.cu"
 VARIANTS = {
     "nopadpair": {API: ["-DULTRA_META_PAD=0", "-DULTRA_META_PAIR=0"]},
     "unroll6": {API: ["-DULTRA_FWD_UNROLL=6", "-DULTRA_FWD_UNROLL_W=4", "-DULTRA_META_PAIR=0"]},
@@ -30,6 +30,8 @@ VARIANTS = {
     "cta1024": {API: ["-DULTRA_CTA_THREADS=1024", "-DULTRA_CTAS_PER_SM=1"]},  # one relation tile per SM -> ~3x the L1
     "cta768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1"]},   # 24 warps, 85 registers, no spills
     "cta768u8": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"]},
+    "cut256": {PLAN: ["-DULTRA_CUT_BLOCK=256"]},
+    "cut1024": {PLAN: ["-DULTRA_CUT_BLOCK=1024"]},
     "pipe768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_PIPE=1"]},
     "pipe512": {API: ["-DULTRA_FWD_PIPE=1"]},
     "pipe1024": {API: ["-DULTRA_CTA_THREADS=1024", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_PIPE=1"]},

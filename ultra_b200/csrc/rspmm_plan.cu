@@ -24,7 +24,10 @@ namespace ultra {
 namespace {
 
 constexpr size_t kAlign = 256;
-constexpr int kCutBlock = 64;    // segments per cutter thread (see cut_walk_block)
+#ifndef ULTRA_CUT_BLOCK
+#define ULTRA_CUT_BLOCK 64
+#endif
+constexpr int kCutBlock = ULTRA_CUT_BLOCK;    // segments per cutter thread (see cut_walk_block)
 constexpr int kPlanCounts = 8;   // ints per order in the device-side result block (cut_finalize_kernel)
 struct CutCounts { int whole, groups, chunks, slots, nlong, nempty, nonempty; };  // per cutter block / running totals
 struct LongRec { int seg, b, e, j, slot0, group0, chunk0, pad; };  // a long segment + where its items / slots go
