@@ -85,7 +85,8 @@ def l2_gather(counters, ms):
             "bytes_per_launch": counters["l2_to_l1_bytes"], "l1_hit_rate": counters.get("l1_hit_rate"),
             "peak_note": "rate of the 4-loads-in-flight gather microbench, NOT a hard ceiling: the two-gather backward pass "
                          "of the same template sustains 8.5 TB/s (profiles/roofline_traffic.json backward_rel); the forward "
-                         "pass is short of bytes in flight (DESIGN.md 3.1)"}
+                         "pass waits on the L2 round trip under load: neither more loads in flight nor fewer L1 wavefronts "
+                         "moved it (DESIGN.md 3.1)"}
 
 
 class ClockSampler:

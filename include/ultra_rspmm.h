@@ -51,6 +51,13 @@ const char *ultra_rspmm_version(void);
  * "smem_tiles": highest shared-memory residency mode the segment kernel may choose (2 = relation tile + gathered tile for
  * small graphs, 1 = relation tile only, 0 = none; default 2) - an experiment knob (0 costs +13 % at FB15k-237 scale).
  * "host_copy_split": row blocks per slab copy in forward_host.
+ * "work_queue": 1 (default) = the persistent CTAs draw their blocks of work from a global ticket counter, 0 = static
+ * round-robin (A/B knob; same results bit for bit).
+ * "plan_relation_runs": read by plan_build.  -1 (default) = graphs whose gathered tile and relation tile are both
+ * shared-memory resident ((num_node + num_relation) * 128 B <= 78 KB: ULTRA's relation graphs) get their segments'
+ * edges sorted by relation type first, and the kernel re-reads a relation slice only when the type changes;
+ * 0 = never, 1 = every graph (measured slower on large graphs: the gathers lose their sweep locality).  The order only
+ * changes the floating-point summation order inside a segment.
  * "bwd_fused_relgrad": 0 (default) = backward is two deterministic gather passes (input_grad by column, relation_grad
  * by relation); 1 = ONE pass over the by-column order that also adds each edge's relation_grad contribution with a
  * 16-byte vector reduction at L2 (red.global.add.v4.f32), like the reference's atomicAdd backward (rspmm.cu:198-209):
@@ -74,7 +81,8 @@ int ultra_rspmm_debug_cut_items(const int *seg_ptr, int num_seg, int *items_out,
  * Test hook: copy one array of a built plan to the host (synchronous).  order: 0 by row, 1 by col, 2 by relation;
  * what: 0 items (int4 x plan_info items), 1 fix list (int4), 2 non-empty segment ids (num_seg + 1 ints, entries past
  * the count are unspecified), 3 segment pointer (num_seg + 1 ints), 4 the device-side counts (8 ints: items, fix entries,
- * long-segment fix entries, slots, non-empty entries, merged groups, other items, edges).  The GPU test-suite compares these with the host
+ * long-segment fix entries, slots, non-empty entries, merged groups, other items, edges), 5 the caller's edge ids in
+ * this order's sequence (num_edge ints; base graph).  The GPU test-suite compares these with the host
  * mirror (ultra_rspmm_debug_cut_items); not used by the product path.
  */
 int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int what, void *host_out, int64_t cap_bytes);

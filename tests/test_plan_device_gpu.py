@@ -69,3 +69,30 @@ def test_device_cutter_equals_host_mirror(cuda_device, name):
         assert plan.info(4 + order) == nslots
         got_ne = device_read(plan, order, 2, S + 1, 1)[:len(nonempty), 0]
         assert np.array_equal(got_ne, nonempty), (name, order, "nonempty")
+
+
+@pytest.mark.parametrize("name", ["tiny", "hub", "zipf 5k", "relation graph"])
+def test_segment_edge_order(cuda_device, name):
+    """Inside a segment the edges are sorted by the gathered node id (sweep locality of the row gathers); graphs small
+    enough for shared-memory-resident tiles ((N + R) * 128 B <= 78 KB) are sorted by relation type first, the order the
+    relation-run reuse of the small-graph kernel needs (include/ultra_rspmm.h, tunable plan_relation_runs).  Either way
+    the sequence is a permutation of the caller's edges, grouped by the primary key."""
+    from ultra_b200.plan import GraphPlan
+    ei, et, N, R = next(g[1:] for g in graphs() if g[0] == name)
+    plan = GraphPlan(ei.to(cuda_device), et.to(cuda_device), N, R)
+    E = ei.shape[1]
+    small = (N + R) * 128 <= 78 * 1024
+    row, col, typ = ei[0].numpy(), ei[1].numpy(), et.numpy()
+    for order in (0, 1, 2):
+        eid = device_read(plan, order, 5, E, 1)[:, 0]
+        assert np.array_equal(np.sort(eid), np.arange(E)), (name, order)
+        if order == 2:
+            keys = (row[eid], typ[eid])                      # np.lexsort: last key is the primary one
+        else:
+            pri, sec = (row, col) if order == 0 else (col, row)
+            keys = (sec[eid], typ[eid], pri[eid]) if small else (sec[eid], pri[eid])
+        k = np.stack(keys[::-1], axis=1).astype(np.int64)    # columns: primary first
+        flat = np.zeros(E, np.int64)
+        for c in range(k.shape[1]):
+            flat = flat * (max(N, R) + 1) + k[:, c]
+        assert np.all(np.diff(flat) >= 0), (name, order, "edges not sorted by %d keys" % k.shape[1])

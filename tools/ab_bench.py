@@ -32,6 +32,9 @@ def child():
 
     d = torch.device("cuda:0")
     lib = _capi.lib()
+    for kv in filter(None, os.environ.get("ULTRA_AB_TUNABLES", "").split(",")):  # e.g. plan_relation_runs=1
+        k, v = kv.split("=")
+        assert lib.ultra_rspmm_set_tunable(k.encode(), int(v)) == 0, lib.ultra_rspmm_last_error()
     # C2 entity graph (Zipf, uniform), a min/max-type op at 32 heads, and the relation graph of the C2 KG (474 nodes,
     # 4 relation rows, ~0.9 M edges: the small-graph kernel variant with the gathered tile in shared memory)
     for alpha, heads, op, bwd, relgraph in ((1.0, 128, "add_mul", True, False), (0.0, 128, "add_mul", False, False),
@@ -57,7 +60,7 @@ def child():
         med, best = time_fn(fwd, warmup=3, iters=15)
         rec = {"alpha": alpha, "heads": heads, "op": op, "relation_graph": relgraph, "N": N, "E": E,
                "fwd_ms": round(med, 4), "fwd_ms_min": round(best, 4),
-               "fwd_sum": checksum(out)}
+               "fwd_sum": checksum(out), "fwd_l1": float(out.double().abs().sum().item())}
         if bwd:
             ig, rg = torch.empty_like(x), torch.empty_like(rel)
 
@@ -67,7 +70,8 @@ def child():
                                               scratch.data_ptr(), scratch.numel(), _stream_ptr(d))
                 assert rc == 0, lib.ultra_rspmm_last_error()
             med, best = time_fn(bw, warmup=2, iters=7)
-            rec.update({"bwd_ms": round(med, 4), "ig_sum": checksum(ig), "rg_sum": checksum(rg)})
+            rec.update({"bwd_ms": round(med, 4), "ig_sum": checksum(ig), "rg_sum": checksum(rg),
+                        "ig_l1": float(ig.double().abs().sum().item()), "rg_l1": float(rg.double().abs().sum().item())})
         print(json.dumps(rec), flush=True)
         del plan
     # fused layer epilogue at C2 size (library default implementation of ultra_nbfnet_update_f32)
@@ -101,9 +105,15 @@ def main():
         for f in sorted(os.listdir(vdir)):
             if f.endswith(".so"):
                 libs[f[len("libultra_rspmm_"):-3]] = os.path.join(vdir, f)
+    # the same libraries again with plan-time tunables (results are then NOT bit-identical: another summation order)
+    tunables = {name: "" for name in libs}
+    for name in (("default", "relreuse") if os.environ.get("ULTRA_AB_RELRUNS") else ()):
+        if name in libs:
+            libs[name + "@relruns"] = libs[name]
+            tunables[name + "@relruns"] = "plan_relation_runs=1"
     results, lines = {}, []
     for name, path in libs.items():
-        env = dict(os.environ, ULTRA_RSPMM_LIB=path)
+        env = dict(os.environ, ULTRA_RSPMM_LIB=path, ULTRA_AB_TUNABLES=tunables[name])
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True,
                                text=True, timeout=args.timeout)

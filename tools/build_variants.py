@@ -30,6 +30,9 @@ VARIANTS = {
     "cta1024": {API: ["-DULTRA_CTA_THREADS=1024", "-DULTRA_CTAS_PER_SM=1"]},  # one relation tile per SM -> ~3x the L1
     "cta768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1"]},   # 24 warps, 85 registers, no spills
     "cta768u8": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_UNROLL=8", "-DULTRA_FWD_UNROLL_W=4"]},
+    "noreuse": {API: ["-DULTRA_REUSE_G1=0"]},                         # the build before the parallel-edge gather reuse
+    "reuse1": {API: ["-DULTRA_REUSE_G1=1"]},                          # reuse carried across the groups of U edges
+    "relreuse": {API: ["-DULTRA_REUSE_REL=1"]},                       # + relation-row reuse (tunable plan_relation_runs=1)
     "cut256": {PLAN: ["-DULTRA_CUT_BLOCK=256"]},
     "cut1024": {PLAN: ["-DULTRA_CUT_BLOCK=1024"]},
     "pipe768": {API: ["-DULTRA_CTA_THREADS=768", "-DULTRA_CTAS_PER_SM=1", "-DULTRA_FWD_PIPE=1"]},

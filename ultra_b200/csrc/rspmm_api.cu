@@ -35,6 +35,8 @@ static_assert(kCtasPerSm != 2 || kCtaThreads != 512 || kSlabSmemLimit == 78 * 10
 std::atomic<int> g_l2_percent{25};        // share of L2 the concurrently gathered tiles may occupy
 std::atomic<int> g_host_copy_split{1};   // forward_host: row blocks (streams) per slab copy
 std::atomic<int> g_bwd_fused_relgrad{0};
+std::atomic<int> g_plan_relation_runs{-1};  // read at plan build: sort a segment's edges by relation type first
+                                            // (-1 = only graphs whose tiles are shared-memory resident, 0 never, 1 always)
 std::atomic<int> g_work_queue{1};       // experiment knob: 1 = ticket work queue (default), 0 = static round-robin
 std::atomic<int> g_smem_tiles{2};       // experiment knob: highest SM mode allowed (2 all, 1 relation tile only, 0 none) // 1 = one backward pass, relation_grad by vector reductions (order-dependent)
 
@@ -44,6 +46,12 @@ template <typename T> bool vec_ok(int64_t D, std::initializer_list<const void *>
         if (p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
     return true;
 }
+}  // namespace
+bool plan_relation_runs(int64_t N, int64_t R) {
+    const int v = g_plan_relation_runs.load();
+    return v < 0 ? (size_t)(N + R) * kTileBytes <= kSlabSmemLimit : v != 0;  // the sm_mode == 2 condition of launch_pass
+}
+namespace {
 
 // ---- one segment pass (tiled kernel + fix-up, or the generic kernel) -------------------------------------
 // heads == 0: flat (rows, D) matrices.  heads > 0: head-major (heads, rows, D / heads) matrices.
@@ -329,9 +337,10 @@ int ultra_rspmm_set_tunable(const char *name, int value) {
     if (n == "host_copy_split") { g_host_copy_split.store(value); return 0; }
     if (n == "bwd_fused_relgrad") { g_bwd_fused_relgrad.store(value != 0); return 0; }
     if (n == "work_queue") { g_work_queue.store(value != 0); return 0; }
+    if (n == "plan_relation_runs") { g_plan_relation_runs.store(value < 0 ? -1 : (value != 0)); return 0; }
     if (n == "smem_tiles") { g_smem_tiles.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (n == "l2_percent") { g_l2_percent.store(value < 1 ? 1 : (value > 100 ? 100 : value)); return 0; }
-    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, smem_tiles, work_queue)");
+    set_error("set_tunable: unknown tunable '" + n + "' (l2_percent, host_copy_split, bwd_fused_relgrad, smem_tiles, work_queue, plan_relation_runs)");
     return 1;
 }
 
@@ -363,7 +372,8 @@ int ultra_rspmm_plan_debug_read(const ultra_rspmm_plan *plan, int order, int wha
         case 2: src = so.nonempty; bytes = (size_t)(so.num_seg + 1) * 4; break;
         case 3: src = so.seg_ptr; bytes = (size_t)(so.num_seg + 1) * 4; break;
         case 4: src = so.counts; bytes = 8 * 4; break;
-        default: set_error("plan_debug_read: what must be 0 (items), 1 (fix), 2 (nonempty), 3 (seg_ptr), 4 (counts)"); return 1;
+        case 5: src = so.eid; bytes = (size_t)plan->E * 4; break;
+        default: set_error("plan_debug_read: what must be 0 (items), 1 (fix), 2 (nonempty), 3 (seg_ptr), 4 (counts), 5 (edge ids)"); return 1;
     }
     if (plan->masked && (what == 0 || what == 1)) bytes = (size_t)cap_bytes;  // exact sizes live on the device (what = 4)
     if ((int64_t)bytes > cap_bytes) { set_error("plan_debug_read: host buffer too small"); return 1; }

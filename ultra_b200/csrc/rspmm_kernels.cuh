@@ -291,6 +291,20 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
     for (int k = 0; k < V; k++) self.v[k] = T(0);
     if (N::self) self = ld_row<T>(self_c, seg, row_bytes);
 
+    // Relation-run reuse, small graphs only (SM == 2: gathered tile AND relation tile in shared memory, so the pass is
+    // bound by shared-memory wavefronts, two LDS.128 per edge-tile).  plan_build sorts such a graph's segments by relation
+    // type first (rspmm_plan.cu), the lane keeps the current relation slice in registers and re-reads it only when the type
+    // changes: ULTRA's relation graph has 4 edge types, so nearly every relation LDS disappears (measured on the
+    // relation graph of the FB15k-237-scale KG, 64 heads: forward 1.20 -> 0.91 ms).  Same values, same order of operations.
+    // NOT applied to the large-graph kernels: there the same trick (and its twin, reusing the gathered row of parallel
+    // edges, 35 % of the Zipf benchmark graph's edges) removed up to a third of the L1 wavefronts and bought nothing
+    // (profiles/r02_run_reuse_ab.txt) - that pass is bound by L2 latency under load, not by the L1 data pipe.
+    constexpr bool kReuseRel = N::rel && SM == 2;
+    unsigned prev_rid = 0xffffffffu;
+    Vec<T> rcur;
+#pragma unroll
+    for (int k = 0; k < V; k++) rcur.v[k] = T(0);
+
     // Stage this item's metadata (<= 64 x 8 bytes) in shared memory with coalesced loads: the hot loop then reads it
     // with a ~30-cycle broadcast LDS instead of a dependent global load, so each group of U edges exposes ONE long
     // latency (the row gather) instead of two (metadata -> gather).  The stall profile was 72 % long_scoreboard.
@@ -372,7 +386,14 @@ __device__ __forceinline__ void walk_items_impl(const SegParams<T> &p, int wi, i
             // relation tile in shared memory: fetch the vector just in time (~30 cycles, other warps cover it) instead
             // of holding U of them in registers - the registers are better spent on row gathers in flight.
             // (b << 7): 128 bytes per relation row of the smem tile; the shift drops the flag bit 31
-            if (N::rel && REL_SMEM) rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
+            if (N::rel && REL_SMEM) {
+                if (kReuseRel) {
+                    const unsigned rid = (unsigned)m[u].y << 7;
+                    if (rid != prev_rid) rcur = lds_vec<T>(rel_q + rid);
+                    prev_rid = rid;
+                    rr[u] = rcur;
+                } else rr[u] = lds_vec<T>(rel_q + ((uint32_t)m[u].y << 7));
+            }
             Vec<T> nxt[NA], rg;
 #pragma unroll
             for (int k = 0; k < V; k++) {

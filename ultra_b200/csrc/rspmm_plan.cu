@@ -112,9 +112,12 @@ __global__ void validate_kernel(const int64_t *__restrict__ ei, const int64_t *_
 // order 0: (row, col)   order 1: (col, row)   order 2: (type, row).
 // The secondary key matters for speed, not correctness: with every segment's edges sorted by the gathered node id,
 // all warps sweep the gathered matrix from low to high rows roughly in step, which is what gives the gathers their
-// L1/L2 temporal locality (measured: grouping by relation type instead costs +40% forward time on a uniform graph).
+// L1/L2 temporal locality (measured: grouping by relation type instead costs +40% forward time on a uniform graph,
+// +20 % on the Zipf one).  Graphs small enough for the gathered tile to sit in shared memory have no such locality to
+// lose: their orders 0 and 1 are (row, type, col) / (col, type, row).
 __global__ void make_keys_kernel(int order, const int64_t *__restrict__ ei, const int64_t *__restrict__ et,
-                                 int64_t E, int64_t N, int64_t R, int sec_bits, unsigned long long *keys, int *vals) {
+                                 int64_t E, int64_t N, int64_t R, int sec_bits, int node_bits, unsigned long long *keys,
+                                 int *vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     // out-of-range values (flagged by validate_kernel; the plan is rejected at the end of the build) are clamped here so
@@ -125,6 +128,10 @@ __global__ void make_keys_kernel(int order, const int64_t *__restrict__ ei, cons
     if (order == 0) { pri = row; sec = col; }
     else if (order == 1) { pri = col; sec = row; }
     else { pri = clampi(et[e], R); sec = row; }
+    // small graphs (tunable "plan_relation_runs"): relation type between the primary and the node key, so that a segment's
+    // edges form runs of one relation type and the kernel re-reads the relation slice only when the type changes
+    // (sec_bits > node_bits only then; see walk_items_impl)
+    if (order != 2 && sec_bits > node_bits) sec |= clampi(et[e], R) << node_bits;
     keys[e] = (pri << sec_bits) | sec;
     vals[e] = (int)e;
 }
@@ -514,10 +521,14 @@ int plan_build(ultra_rspmm_plan **out, const int64_t *edge_index, const int64_t 
     // and the plan is rejected after the ONE synchronisation at the end.
     for (int o = 0; o < 3; o++) {
         SegOrder &so = plan->ord[o];
-        const int sec_bits = bits_for(std::max<int64_t>(N, 2));
+        const int node_bits = bits_for(std::max<int64_t>(N, 2));
         const int pri_bits = bits_for(std::max<int64_t>(S[o], 2));
+        int sec_bits = node_bits;
+        if (o != 2 && plan_relation_runs(N, R) && pri_bits + node_bits + bits_for(std::max<int64_t>(R, 2)) <= 64)
+            sec_bits += bits_for(std::max<int64_t>(R, 2));
         if (E > 0) {
-            make_keys_kernel<<<blocks, threads, 0, stream>>>(o, edge_index, edge_type, E, N, R, sec_bits, keysA, valsA);
+            make_keys_kernel<<<blocks, threads, 0, stream>>>(o, edge_index, edge_type, E, N, R, sec_bits, node_bits, keysA,
+                                                             valsA);
             CUDA_TRY(cudaGetLastError());
             cub::DoubleBuffer<unsigned long long> dk(keysA, keysB);
             cub::DoubleBuffer<int> dv(valsA, valsB);

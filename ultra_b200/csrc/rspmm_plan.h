@@ -63,6 +63,7 @@ struct ultra_rspmm_plan {
 
 namespace ultra {
 void set_error(const std::string &msg);
+bool plan_relation_runs(int64_t N, int64_t R);  // rspmm_api.cu: relation-first secondary sort key for this graph?
 size_t plan_workspace_bytes(int64_t N, int64_t E, int64_t R);
 int cut_items_host(const int *seg_ptr, int num_seg, int *items_out, int64_t items_cap, int *num_items, int *fix_out,
                    int64_t fix_cap, int *num_fix, int *num_fix_long, int *num_slots, int *nonempty_out,
