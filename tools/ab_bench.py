@@ -96,6 +96,8 @@ def main():
     ap.add_argument("--child", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--timeout", type=int, default=150)
+    ap.add_argument("--tunable-sets", default="", help="run the DEFAULT library again under these tunables, e.g. "
+                    "'pf0:l2_prefetch_tiles=0 pf8:l2_prefetch_tiles=8' (name:k=v[,k=v])")
     args = ap.parse_args()
     if args.child:
         return child()
@@ -111,6 +113,10 @@ def main():
         if name in libs:
             libs[name + "@relruns"] = libs[name]
             tunables[name + "@relruns"] = "plan_relation_runs=1"
+    for item in args.tunable_sets.split():
+        name, kv = item.split(":")
+        libs["default@" + name] = libs["default"]
+        tunables["default@" + name] = kv
     results, lines = {}, []
     for name, path in libs.items():
         env = dict(os.environ, ULTRA_RSPMM_LIB=path, ULTRA_AB_TUNABLES=tunables[name])

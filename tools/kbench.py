@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--peak", type=float, default=6583.2)
     ap.add_argument("--l2-percent", type=int, default=0)
     ap.add_argument("--sm-limit", type=int, default=0)
+    ap.add_argument("--tunable", action="append", default=[], help="name=value for ultra_rspmm_set_tunable (repeatable)")
     ap.add_argument("--work-queue", type=int, default=-1, help="experiment: 1 ticket work queue (default), 0 static round-robin")
     ap.add_argument("--smem-tiles", type=int, default=-1, help="experiment: highest smem residency mode (2 / 1 / 0)")
     ap.add_argument("--mask-frac", type=float, default=0.0,
@@ -45,6 +46,9 @@ def main():
     args = ap.parse_args()
     d = torch.device("cuda:0")
     lib = _capi.lib()
+    for kv in args.tunable:
+        k, v = kv.split("=")
+        _capi.set_tunable(k, int(v))
     if args.work_queue >= 0:
         _capi.set_tunable("work_queue", args.work_queue)
     if args.smem_tiles >= 0:
