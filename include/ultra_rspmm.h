@@ -266,6 +266,18 @@ int ultra_nbfnet_update_bwd_f32(const float *out_grad, const float *z, const flo
 int ultra_relation_project_f32(const float *x, const float *w1_t, const float *b1, const float *w2_t, const float *b2,
                                float *out, int64_t num_rows, int64_t dim, int64_t num_layers, void *stream);
 
+/*
+ * The entity model's scoring MLP over every (query, entity) pair in ONE pass, fp32:
+ *     out[m] = w2 . relu( W1h . h[m, :] + qb[m / rows_per_head, :] ) + b2                    m < num_rows
+ * replaces  mlp(cat[h, query])  of /root/reference/ultra/models.py:166-170,202-208 (Linear(128,128) -> ReLU -> Linear(128,1))
+ * for the all-tails evaluation protocol (tasks.py:79-91): the first Linear is split into its h half W1h (128, 64) and its
+ * query half, whose product with the query (+ bias) the caller passes as qb (num_heads, 128).
+ *   h (num_rows, 64) = the (B, N, 64) final states, rows_per_head = N;  w1h_t (64, 128) = W1h TRANSPOSED ([k][n]);
+ *   w2 (128);  b2 (1, on the device: no host read, CUDA-graph capturable);  out (num_rows).  Only dim == 64, hidden == 128; other sizes return an error and the caller keeps its MLP.
+ */
+int ultra_score_head_f32(const float *h, const float *w1h_t, const float *qb, const float *w2, const float *b2,
+                         float *out, int64_t num_rows, int64_t rows_per_head, int64_t dim, int64_t hidden, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

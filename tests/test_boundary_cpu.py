@@ -19,7 +19,7 @@ def capi():
 
 def test_header_symbols_exported(capi):
     header = open(os.path.join(ROOT, "include", "ultra_rspmm.h")).read()
-    declared = set(re.findall(r"\b(ultra_(?:rspmm|nbfnet|relation)_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(ultra_(?:rspmm|nbfnet|relation|score)_[a-z0-9_]+)\s*\(", header))
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
     handle = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:

@@ -36,6 +36,7 @@ SYMBOLS = {
     "ultra_rspmm_backward_heads": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _vp,
                                           _sz, _vp]),
     "ultra_relation_project_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "ultra_score_head_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "ultra_nbfnet_update_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float, _int, _int,
                                        _int, _int, _vp]),
     "ultra_nbfnet_update_train_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_float,

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libultra_rspmm.so")
-SOURCES = ["rspmm_api.cu", "rspmm_plan.cu", "nbfnet_update.cu", "relation_project.cu"]
+SOURCES = ["rspmm_api.cu", "rspmm_plan.cu", "nbfnet_update.cu", "relation_project.cu", "score_head.cu"]
 HEADERS = ["rspmm_kernels.cuh", "rspmm_plan.h", os.path.join("..", "..", "include", "ultra_rspmm.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

@@ -131,6 +131,35 @@ def relation_project(rel_repr, projections):
     return out
 
 
+def score_head_ok(h, mlp):
+    """`mlp` is Sequential(Linear(128,128), ReLU, Linear(128,1)) (models.py:114-118 with feature_dim 128) on fp32 CUDA
+    states (B, N, 64); inference only (the kernel has no backward: under autograd the caller keeps its eager MLP)."""
+    return (h.is_cuda and h.dtype == torch.float32 and h.dim() == 3 and h.shape[-1] == 64 and not torch.is_grad_enabled()
+            and len(mlp) == 3 and isinstance(mlp[0], torch.nn.Linear) and isinstance(mlp[1], torch.nn.ReLU)
+            and isinstance(mlp[2], torch.nn.Linear) and mlp[0].weight.shape == (128, 128) and mlp[2].weight.shape == (1, 128)
+            and mlp[0].bias is not None and mlp[2].bias is not None and mlp[0].weight.dtype == torch.float32)
+
+
+def score_head(h, query, mlp):
+    """Scores of every entity as the tail of every query, (B, N), in one pass over the final states h (B, N, 64):
+    mlp(cat[h, query]) of models.py:166-170,202-208 with the first Linear split into its h and query halves."""
+    lib = _capi.lib()
+    B, N, d = h.shape
+    h = h.contiguous()
+    with torch.no_grad():
+        w1 = mlp[0].weight
+        qb = torch.addmm(mlp[0].bias, query, w1[:, d:].t()).contiguous()     # (B, 128): query half + bias
+        w1h_t = w1[:, :d].t().contiguous()                                    # (64, 128) [k][n]
+        w2 = mlp[2].weight.reshape(-1).contiguous()
+        b2 = mlp[2].bias.contiguous()
+    out = h.new_empty(B, N)
+    with torch.cuda.device(h.device):
+        rc = lib.ultra_score_head_f32(h.data_ptr(), w1h_t.data_ptr(), qb.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                      out.data_ptr(), B * N, N, d, w1.shape[0], _stream_ptr(h.device))
+    _capi.check(rc, "ultra_score_head_f32")
+    return out
+
+
 def nbfnet_update_ok(x, u, linear, activation, layer_norm=None):
     """Shapes / dtypes the fused epilogue covers.  With autograd recording, the training variant (which needs LayerNorm
     and the Linear bias) is used; otherwise the inference kernel."""

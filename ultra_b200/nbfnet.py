@@ -185,6 +185,8 @@ class UltraNBFNet(nn.Module):
         """Scores of EVERY entity as the tail (the evaluation protocol, tasks.py:79-91: t_index = arange(N)) -> (B, N).
         mlp[0] on cat[h, q] is split into its h and q halves, so the (B, N, 2d) concatenation is never built."""
         mlp = self.entity_model.mlp
+        if fused.score_head_ok(h, mlp):
+            return fused.score_head(h, query, mlp)   # one pass over h, the hidden layer never reaches HBM
         if len(mlp) != 3:
             t_index = torch.arange(h.shape[1], device=h.device).expand(h.shape[0], -1)
             return self.score(h, query, t_index)
