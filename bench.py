@@ -700,6 +700,10 @@ def bench_strong(name, device, world, rank, dist, timeit):
         # over 1/N of the columns); aggregate over the ranks = E * B / (max-over-ranks time)
         info["rspmm_edge_heads_per_sec_aggregate"] = int(ei.shape[1]) * B / (info["rspmm_ms_per_gpu"] * 1e-3)
         del rel_l, x_l, out_l
+        # (a2) the all-tails scoring MLP at the local head count (ultra_score_head_f32; models.py:166-170,202-208)
+        h_s, q_s = torch.randn(hi - lo, N, DIM, device=device), torch.randn(hi - lo, DIM, device=device)
+        info["score_head_ms_per_gpu"] = timeit(lambda: model.score_all(h_s, q_s), reps=10, warm=3)
+        del h_s, q_s
         # (b) the sharded forward, captured as ONE CUDA graph per rank, + the score all-gather on the timed path
         local = CudaGraphRunner(fwd, h_index[lo:hi], r_index[lo:hi])
         scores = torch.empty(B, N, device=device)
