@@ -117,6 +117,29 @@ def test_tunables_are_host_only_and_validated(capi):
     assert _capi.lib().ultra_rspmm_plan_set_sm_limit(None, 140) != 0  # null plan -> error code, no crash
     with pytest.raises(RuntimeError, match="unknown tunable"):  # measured in round 2 (no gain at any size) and removed
         _capi.set_tunable("item_edges", 16)
+    for name in ("l2_prefetch_tiles", "l2_prefetch_copies"):    # same: measured (profiles/r02_l2_prefetch_ab.txt), removed
+        with pytest.raises(RuntimeError, match="unknown tunable"):
+            _capi.set_tunable(name, 4)
+    for value in (1, 0, -1):                                     # plan-time order of small graphs; -1 = the default rule
+        _capi.set_tunable("plan_relation_runs", value)
+    _capi.set_tunable("work_queue", 1)
+
+
+def test_score_head_entry_point_validates_without_a_gpu(capi):
+    """ultra_score_head_f32 rejects unsupported sizes / null or misaligned pointers before touching the device, and the
+    Python gate keeps the eager MLP for anything it does not cover (CPU tensors, autograd, other layer sizes)."""
+    import torch
+    from ultra_b200 import _capi, fused
+    lib = _capi.lib()
+    assert lib.ultra_score_head_f32(None, None, None, None, None, None, 4, 4, 32, 128, None) == 1
+    assert b"dim == 64" in lib.ultra_rspmm_last_error()
+    assert lib.ultra_score_head_f32(None, None, None, None, None, None, 4, 0, 64, 128, None) == 1
+    assert lib.ultra_score_head_f32(None, None, None, None, None, None, 4, 4, 64, 128, None) == 1
+    assert b"non-null" in lib.ultra_rspmm_last_error()
+    assert lib.ultra_score_head_f32(None, None, None, None, None, None, 0, 4, 64, 128, None) == 0   # nothing to do
+    mlp = torch.nn.Sequential(torch.nn.Linear(128, 128), torch.nn.ReLU(), torch.nn.Linear(128, 1))
+    with torch.no_grad():
+        assert not fused.score_head_ok(torch.zeros(2, 5, 64), mlp)          # CPU tensor: not this library's business
 
 
 def test_plain_c_consumer(capi, tmp_path):
